@@ -1,0 +1,448 @@
+// pai_core.cuh -- multi-precision primitives of the B200 Paillier engine.
+//
+// One THREAD owns one big integer ("instance").  Numbers are little-endian arrays of 32-bit limbs
+// grouped in TILES of 8 limbs (256 bit).  Operands live in shared memory in an interleaved layout
+// (quad q of thread t at  base[q * nthreads + t], 16 bytes each) so that every LDS.128/STS.128 of
+// a warp is conflict free; tile products run in registers as chains of IMAD.WIDE.U32(.X) that
+// ptxas fuses from  mad.lo.cc / madc.hi.cc  pairs (verified with cuobjdump on sm_100a).
+//
+// Everything in this header is written once and compiled twice:
+//   * by nvcc for sm_100a (the product), and
+//   * by g++ with -DPAI_HOSTSIM (tests/hostsim: a TEST-ONLY build that runs the very same
+//     templates on the CPU, one simulated thread at a time, so the algorithms can be checked
+//     against the oracle in the GPU-less build container).  The product never loads that build.
+//
+// Reference semantics implemented on top of these primitives (see pai_kernels.cuh):
+//   powmod  phe/util.py:38-50      mulmod  phe/util.py:53-64      invert  phe/util.py:85-103
+#pragma once
+#include <stdint.h>
+
+#if defined(PAI_HOSTSIM)
+#define PAI_DEV static inline
+#define PAI_FN static
+#define PAI_HD static inline
+#define PAI_MEM inline
+struct pai_u4 { uint32_t x, y, z, w; };
+typedef pai_u4 u4;
+#define PAI_UNROLL
+#else
+#define PAI_DEV __device__ __forceinline__
+#define PAI_FN __device__ __noinline__
+#define PAI_HD __host__ __device__ __forceinline__
+#define PAI_MEM __device__ __forceinline__
+typedef uint4 u4;
+#define PAI_UNROLL _Pragma("unroll")
+#endif
+
+namespace pai {
+
+static const int TILE = 8;  // limbs per tile
+
+// ------------------------------------------------------------------------------------------------
+// Operand descriptor: quad q (4 limbs) is at p[q * s].
+//   per-thread operand in the interleaved shared/global layout: p = base + tid, s = nthreads
+//   broadcast operand (per-key constant, same for all threads):  p = base,       s = 1
+struct Opnd {
+  u4* p;
+  int s;
+};
+
+PAI_DEV void ld_tile(const Opnd& o, int t, uint32_t a[8]) {
+  u4 q0 = o.p[(2 * t) * o.s];
+  u4 q1 = o.p[(2 * t + 1) * o.s];
+  a[0] = q0.x; a[1] = q0.y; a[2] = q0.z; a[3] = q0.w;
+  a[4] = q1.x; a[5] = q1.y; a[6] = q1.z; a[7] = q1.w;
+}
+PAI_DEV void st_tile(const Opnd& o, int t, const uint32_t a[8]) {
+  u4 q0, q1;
+  q0.x = a[0]; q0.y = a[1]; q0.z = a[2]; q0.w = a[3];
+  q1.x = a[4]; q1.y = a[5]; q1.z = a[6]; q1.w = a[7];
+  o.p[(2 * t) * o.s] = q0;
+  o.p[(2 * t + 1) * o.s] = q1;
+}
+PAI_DEV void zero_tile(const Opnd& o, int t) {
+  u4 z; z.x = z.y = z.z = z.w = 0;
+  o.p[(2 * t) * o.s] = z;
+  o.p[(2 * t + 1) * o.s] = z;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Carry-chain primitives.  Each is ONE asm block so the carry flag never crosses a statement.
+
+// X[0..7] (four 64-bit aligned pairs) += {a0,a1,a2,a3} * b at pair offsets 0,2,4,6; carry-out -> cw
+PAI_DEV void mac_chain4(uint32_t* X, uint32_t& cw, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+#if !defined(PAI_HOSTSIM)
+  asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+      "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+      "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+      "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+      "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+      "addc.u32 %8, %8, 0;"
+      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(cw)
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+#else
+  const uint32_t av[4] = {a0, a1, a2, a3};
+  uint32_t c = 0;
+  for (int i = 0; i < 4; i++) {
+    unsigned __int128 v = ((unsigned __int128)(((uint64_t)X[2 * i + 1] << 32) | X[2 * i])) + (uint64_t)av[i] * b + c;
+    X[2 * i] = (uint32_t)v;
+    X[2 * i + 1] = (uint32_t)(v >> 32);
+    c = (uint32_t)(v >> 64);
+  }
+  cw += c;
+#endif
+}
+
+// r[0..7] = a[0..7] + b[0..7]; returns carry-out (0/1)
+PAI_DEV uint32_t add8(uint32_t r[8], const uint32_t a[8], const uint32_t b[8]) {
+  uint32_t c;
+#if !defined(PAI_HOSTSIM)
+  asm("add.cc.u32 %0, %9, %17;\n\t"
+      "addc.cc.u32 %1, %10, %18;\n\t"
+      "addc.cc.u32 %2, %11, %19;\n\t"
+      "addc.cc.u32 %3, %12, %20;\n\t"
+      "addc.cc.u32 %4, %13, %21;\n\t"
+      "addc.cc.u32 %5, %14, %22;\n\t"
+      "addc.cc.u32 %6, %15, %23;\n\t"
+      "addc.cc.u32 %7, %16, %24;\n\t"
+      "addc.u32 %8, 0, 0;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+  uint64_t cc = 0;
+  for (int i = 0; i < 8; i++) { cc += (uint64_t)a[i] + b[i]; r[i] = (uint32_t)cc; cc >>= 32; }
+  c = (uint32_t)cc;
+#endif
+  return c;
+}
+
+// r = a + b + cin ; returns carry-out.  cin in {0,1}
+PAI_DEV uint32_t add8c(uint32_t r[8], const uint32_t a[8], const uint32_t b[8], uint32_t cin) {
+  uint32_t c;
+#if !defined(PAI_HOSTSIM)
+  asm("add.cc.u32 %8, %25, 0xffffffff;\n\t"   // sets CF = cin
+      "addc.cc.u32 %0, %9, %17;\n\t"
+      "addc.cc.u32 %1, %10, %18;\n\t"
+      "addc.cc.u32 %2, %11, %19;\n\t"
+      "addc.cc.u32 %3, %12, %20;\n\t"
+      "addc.cc.u32 %4, %13, %21;\n\t"
+      "addc.cc.u32 %5, %14, %22;\n\t"
+      "addc.cc.u32 %6, %15, %23;\n\t"
+      "addc.cc.u32 %7, %16, %24;\n\t"
+      "addc.u32 %8, 0, 0;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=&r"(c)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(cin));
+#else
+  uint64_t cc = cin;
+  for (int i = 0; i < 8; i++) { cc += (uint64_t)a[i] + b[i]; r[i] = (uint32_t)cc; cc >>= 32; }
+  c = (uint32_t)cc;
+#endif
+  return c;
+}
+
+// r = a - b - bin ; returns borrow-out (0/1).  bin in {0,1}
+PAI_DEV uint32_t sub8b(uint32_t r[8], const uint32_t a[8], const uint32_t b[8], uint32_t bin) {
+  uint32_t bo;
+#if !defined(PAI_HOSTSIM)
+  asm("sub.cc.u32 %8, 0, %25;\n\t"            // 0 - bin : borrow set iff bin == 1
+      "subc.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"                     // 0 - 0 - borrow  -> 0 or 0xffffffff
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=&r"(bo)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(bin));
+  bo &= 1u;
+#else
+  uint64_t bb = bin;
+  for (int i = 0; i < 8; i++) {
+    uint64_t d = (uint64_t)a[i] - b[i] - bb;
+    r[i] = (uint32_t)d;
+    bb = (d >> 63) & 1;
+  }
+  bo = (uint32_t)bb;
+#endif
+  return bo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column accumulator.  Value = sum_i (E[i] + O[i] + C[i]) * 2^(32 i).
+//   E : targets of chains that start on an even column (pairs (0,1),(2,3),...)
+//   O : targets of chains that start on an odd column  (pairs (1,2),(3,4),...)
+//   C : small counters that collect the carry-out of every chain (never a product target, so they
+//       cannot overflow); keeping them separate makes every tile MAC exact without rippling.
+struct Acc {
+  uint32_t E[16], O[16], C[17];
+};
+
+PAI_DEV void acc_clear(Acc& A) {
+  PAI_UNROLL
+  for (int i = 0; i < 16; i++) { A.E[i] = 0; A.O[i] = 0; A.C[i] = 0; }
+  A.C[16] = 0;
+}
+
+// A += a[0..7] * b[0..7]   (64 wide MACs + 16 carry captures)
+PAI_DEV void tile_mac(Acc& A, const uint32_t a[8], const uint32_t b[8]) {
+  PAI_UNROLL
+  for (int j = 0; j < 8; j++) {
+    if ((j & 1) == 0) {
+      mac_chain4(&A.E[j], A.C[j + 8], a[0], a[2], a[4], a[6], b[j]);
+      mac_chain4(&A.O[j + 1], A.C[j + 9], a[1], a[3], a[5], a[7], b[j]);
+    } else {
+      mac_chain4(&A.O[j], A.C[j + 8], a[0], a[2], a[4], a[6], b[j]);
+      mac_chain4(&A.E[j + 1], A.C[j + 9], a[1], a[3], a[5], a[7], b[j]);
+    }
+  }
+}
+
+// v = low 8 limbs of the accumulator value; their carry is pushed into C[8]
+PAI_DEV void acc_resolve_low(Acc& A, uint32_t v[8]) {
+  uint32_t t[8];
+  uint32_t c1 = add8(t, A.E, A.O);
+  uint32_t c2 = add8(v, t, A.C);
+  A.C[8] += c1 + c2;
+}
+
+// v = low 8 limbs of the accumulator value WITHOUT recording their carry (the limbs stay in place;
+// a later acc_resolve_low over the same limbs accounts for the carry exactly once)
+PAI_DEV void acc_peek_low(const Acc& A, uint32_t v[8]) {
+  uint32_t t[8];
+  add8(t, A.E, A.O);
+  add8(v, t, A.C);
+}
+
+// A.low8 += d[0..7]  (carry captured in C[8])
+PAI_DEV void acc_add_low(Acc& A, const uint32_t d[8]) {
+  uint32_t t[8];
+  uint32_t c = add8(t, A.E, d);
+  PAI_UNROLL
+  for (int i = 0; i < 8; i++) A.E[i] = t[i];
+  A.C[8] += c;
+}
+
+// A >>= 256 bits (the low 8 limbs must already have been consumed)
+PAI_DEV void acc_shift8(Acc& A) {
+  PAI_UNROLL
+  for (int i = 0; i < 8; i++) {
+    A.E[i] = A.E[i + 8]; A.E[i + 8] = 0;
+    A.O[i] = A.O[i + 8]; A.O[i + 8] = 0;
+    A.C[i] = A.C[i + 8]; A.C[i + 8] = 0;
+  }
+  A.C[8] = A.C[16];
+  A.C[16] = 0;
+}
+
+// m = (v * w) mod 2^256
+PAI_DEV void mul_lo8(uint32_t m[8], const uint32_t v[8], const uint32_t w[8]) {
+  Acc T;
+  acc_clear(T);
+  tile_mac(T, v, w);
+  acc_resolve_low(T, m);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Whole-number helpers on interleaved operands (NT tiles each).
+
+// borrow of (a - b); nothing stored
+template <int NT>
+PAI_DEV uint32_t big_sub_borrow(const Opnd& a, const Opnd& b) {
+  uint32_t bo = 0;
+  for (int t = 0; t < NT; t++) {
+    uint32_t x[8], y[8], r[8];
+    ld_tile(a, t, x); ld_tile(b, t, y);
+    bo = sub8b(r, x, y, bo);
+  }
+  return bo;
+}
+
+// out = a - (b & mask)   (mask = 0 or 0xffffffff); returns borrow
+template <int NT>
+PAI_DEV uint32_t big_sub_masked(const Opnd& out, const Opnd& a, const Opnd& b, uint32_t mask) {
+  uint32_t bo = 0;
+  for (int t = 0; t < NT; t++) {
+    uint32_t x[8], y[8], r[8];
+    ld_tile(a, t, x); ld_tile(b, t, y);
+    PAI_UNROLL
+    for (int i = 0; i < 8; i++) y[i] &= mask;
+    bo = sub8b(r, x, y, bo);
+    st_tile(out, t, r);
+  }
+  return bo;
+}
+
+// out = a + (b & mask); returns carry
+template <int NT>
+PAI_DEV uint32_t big_add_masked(const Opnd& out, const Opnd& a, const Opnd& b, uint32_t mask) {
+  uint32_t c = 0;
+  for (int t = 0; t < NT; t++) {
+    uint32_t x[8], y[8], r[8];
+    ld_tile(a, t, x); ld_tile(b, t, y);
+    PAI_UNROLL
+    for (int i = 0; i < 8; i++) y[i] &= mask;
+    c = add8c(r, x, y, c);
+    st_tile(out, t, r);
+  }
+  return c;
+}
+
+// x = x - N if (force || x >= N)    -> canonical residue when x < 2N (or x + force*2^(256NT) < 2N)
+template <int NT>
+PAI_DEV void big_cond_sub(const Opnd& x, const Opnd& N, uint32_t force) {
+  uint32_t bo = big_sub_borrow<NT>(x, N);
+  uint32_t need = (force | (bo ^ 1u)) & 1u;
+  big_sub_masked<NT>(x, x, N, 0u - need);
+}
+
+template <int NT>
+PAI_DEV void big_copy(const Opnd& dst, const Opnd& src) {
+  for (int q = 0; q < 2 * NT; q++) dst.p[q * dst.s] = src.p[q * src.s];
+}
+
+template <int NT>
+PAI_DEV uint32_t big_is_zero(const Opnd& a) {
+  uint32_t acc = 0;
+  for (int q = 0; q < 2 * NT; q++) { u4 v = a.p[q * a.s]; acc |= v.x | v.y | v.z | v.w; }
+  return acc == 0 ? 1u : 0u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Plain product, column (product) scanning over tiles:
+//   out[0..NCOL) = low NCOL tiles of  (a * b + addend),  a: NTA tiles, b: NTB tiles, addend < 2^32
+template <int NTA, int NTB, int NCOL>
+PAI_DEV void big_mul(const Opnd& out, const Opnd& a, const Opnd& b, uint32_t addend) {
+  Acc acc;
+  acc_clear(acc);
+  acc.E[0] = addend;
+  for (int k = 0; k < NCOL; k++) {
+    int lo = k - NTB + 1 > 0 ? k - NTB + 1 : 0;
+    int hi = k < NTA - 1 ? k : NTA - 1;
+    for (int i = lo; i <= hi; i++) {
+      uint32_t x[8], y[8];
+      ld_tile(a, i, x); ld_tile(b, k - i, y);
+      tile_mac(acc, x, y);
+    }
+    uint32_t v[8];
+    acc_resolve_low(acc, v);
+    st_tile(out, k, v);
+    acc_shift8(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Montgomery multiplication, tile-level finely integrated product scanning (R = 2^(256 NT)):
+//   out = a * b / R mod N, canonical (< N) provided a*b < R*N.
+//   `out` doubles as the store for the quotient tiles m_i (dead before the result tile that
+//   replaces them is written), so out must not alias a or b.  N is a broadcast operand,
+//   NI = tile holding -N^-1 mod 2^256.
+template <int NT>
+PAI_FN void mont_mul(Opnd out, Opnd a, Opnd b, Opnd N, Opnd NI) {
+  Acc acc;
+  acc_clear(acc);
+  uint32_t n0[8], ninv[8];
+  ld_tile(N, 0, n0);
+  ld_tile(NI, 0, ninv);
+  for (int k = 0; k < 2 * NT; k++) {
+    int lo = k - NT + 1 > 0 ? k - NT + 1 : 0;
+    int hi = k < NT ? k - 1 : NT - 1;
+    // terms that have both a product and a reduction partner: i in [lo, hi], j = k - i >= 1
+    for (int i = lo; i <= hi; i++) {
+      uint32_t x[8], y[8];
+      ld_tile(a, i, x); ld_tile(b, k - i, y);
+      tile_mac(acc, x, y);
+      ld_tile(out, i, x); ld_tile(N, k - i, y);
+      tile_mac(acc, x, y);
+    }
+    uint32_t v[8];
+    if (k < NT) {
+      uint32_t x[8], y[8], m[8];
+      ld_tile(a, k, x); ld_tile(b, 0, y);
+      tile_mac(acc, x, y);
+      acc_peek_low(acc, v);
+      mul_lo8(m, v, ninv);
+      st_tile(out, k, m);
+      tile_mac(acc, m, n0);
+      acc_resolve_low(acc, v);          // == 0 by construction; pushes the carry into C[8]
+    } else {
+      acc_resolve_low(acc, v);
+      st_tile(out, k - NT, v);
+    }
+    acc_shift8(acc);
+  }
+  uint32_t ovf = acc.E[0] + acc.O[0] + acc.C[0];
+  big_cond_sub<NT>(out, N, ovf);
+}
+
+// Montgomery squaring: out = a*a/R mod N.  Off-diagonal tile products are accumulated once in a
+// second accumulator S, doubled on the way into the main accumulator (136 instead of 256 product
+// tiles at NT = 16).
+template <int NT>
+PAI_FN void mont_sqr(Opnd out, Opnd a, Opnd N, Opnd NI) {
+  Acc acc, S;
+  acc_clear(acc);
+  acc_clear(S);
+  uint32_t n0[8], ninv[8];
+  ld_tile(N, 0, n0);
+  ld_tile(NI, 0, ninv);
+  uint32_t topbit = 0;
+  for (int k = 0; k < 2 * NT; k++) {
+    int lo = k - NT + 1 > 0 ? k - NT + 1 : 0;
+    int hi = k < NT ? k - 1 : NT - 1;
+    // off-diagonal pairs i < j = k - i  <=>  i <= (k-1)/2
+    int hs = (k - 1) / 2;
+    if (k == 0) hs = -1;
+    for (int i = lo; i <= hs; i++) {
+      uint32_t x[8], y[8];
+      ld_tile(a, i, x); ld_tile(a, k - i, y);
+      tile_mac(S, x, y);
+    }
+    // reduction partners m_i * N_(k-i), i in [lo, hi]
+    for (int i = lo; i <= hi; i++) {
+      uint32_t x[8], y[8];
+      ld_tile(out, i, x); ld_tile(N, k - i, y);
+      tile_mac(acc, x, y);
+    }
+    if ((k & 1) == 0) {
+      uint32_t x[8];
+      ld_tile(a, k >> 1, x);
+      tile_mac(acc, x, x);
+    }
+    // main += 2 * (low tile of S)
+    {
+      uint32_t d[8], d2[8];
+      acc_resolve_low(S, d);
+      acc_shift8(S);
+      d2[0] = (d[0] << 1) | topbit;
+      PAI_UNROLL
+      for (int i = 1; i < 8; i++) d2[i] = (d[i] << 1) | (d[i - 1] >> 31);
+      topbit = d[7] >> 31;
+      acc_add_low(acc, d2);
+    }
+    uint32_t v[8];
+    if (k < NT) {
+      uint32_t m[8];
+      acc_peek_low(acc, v);
+      mul_lo8(m, v, ninv);
+      st_tile(out, k, m);
+      tile_mac(acc, m, n0);
+      acc_resolve_low(acc, v);
+    } else {
+      acc_resolve_low(acc, v);
+      st_tile(out, k - NT, v);
+    }
+    acc_shift8(acc);
+  }
+  uint32_t ovf = acc.E[0] + acc.O[0] + acc.C[0] + topbit;
+  big_cond_sub<NT>(out, N, ovf);
+}
+
+}  // namespace pai

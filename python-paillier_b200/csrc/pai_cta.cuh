@@ -1,0 +1,192 @@
+// pai_cta.cuh -- CTA-level bodies of the kernels: shared-memory map, persistent chunk loop.
+//
+// Shared memory map of every kernel:   [ constants (broadcast operands) | buf0 | buf1 | buf2 (| buf3) ]
+// with each buffer holding 2*NT quads for each of the CTA's threads in the interleaved layout.
+// A body has two phases separated by a CTA barrier: phase 0 copies the per-key constants into
+// shared memory cooperatively, phase 1 is the per-thread persistent loop (no barriers: threads are
+// independent).  The __global__ kernels in pai_engine.cu call phase 0, __syncthreads(), phase 1;
+// tests/hostsim calls phase 0 for every simulated thread, then phase 1 for every simulated thread.
+#pragma once
+#include "pai_kernels.cuh"
+
+namespace pai {
+
+struct CtaId {
+  int tid, nthr, cta, ncta;
+};
+
+// phase 0: constants -> shared
+PAI_DEV void cta_load_consts(u4* smem, const CtaId& id, const uint32_t* src, int nquads) {
+  const u4* s = (const u4*)src;
+  for (int i = id.tid; i < nquads; i += id.nthr) smem[i] = s[i];
+}
+
+template <int NT>
+PAI_DEV void cta_bufs(Opnd* buf, int nbuf, u4* smem, int const_quads, const CtaId& id) {
+  for (int b = 0; b < nbuf; b++) {
+    buf[b].p = smem + const_quads + b * (2 * NT) * id.nthr + id.tid;
+    buf[b].s = id.nthr;
+  }
+}
+
+template <int NT, int W>
+PAI_DEV Opnd cta_table(u4* tbl, const CtaId& id) {
+  Opnd t;
+  t.p = tbl + (size_t)id.cta * ((size_t)(1 << W) * 2 * NT * id.nthr) + id.tid;
+  t.s = id.nthr;
+  return t;
+}
+
+// ---- encrypt.  consts = [ blob(n^2) | n (4*NT limbs) ]
+template <int NT>
+PAI_DEV int enc_const_quads() { return mc_limbs(NT) / 4 + NT; }
+
+template <int NT, int W>
+PAI_DEV void cta_encrypt(u4* smem, const CtaId& id, int nwin, const uint32_t* m, const uint32_t* r, uint32_t* out,
+                         long batch, u4* tbl) {
+  ModC mc;
+  modc_bind(mc, smem, NT);
+  PowEnv<NT> E;
+  cta_bufs<NT>(E.buf, 3, smem, enc_const_quads<NT>(), id);
+  E.tbl = cta_table<NT, W>(tbl, id);
+  E.mc = &mc;
+  Opnd nbc{smem + mc_limbs(NT) / 4, 1};
+  const uint32_t* e = (const uint32_t*)(smem + mc_limbs(NT) / 4);
+  const int ln = 4 * NT, lc = 8 * NT;
+  for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
+    long g = chunk * id.nthr + id.tid;
+    bool store = g < batch;
+    if (!store) g = batch - 1;
+    prog_encrypt<NT, W>(E, nbc, e, ln, nwin, m + g * ln, r + g * ln, out + g * lc, store);
+  }
+}
+
+// ---- mulmod.  consts = [ blob ]
+template <int NT>
+PAI_DEV void cta_mulmod(u4* smem, const CtaId& id, const uint32_t* a, const uint32_t* b, uint32_t* out, long batch) {
+  ModC mc;
+  modc_bind(mc, smem, NT);
+  Opnd buf[3];
+  cta_bufs<NT>(buf, 3, smem, mc_limbs(NT) / 4, id);
+  const int l = 8 * NT;
+  for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
+    long g = chunk * id.nthr + id.tid;
+    bool store = g < batch;
+    if (!store) g = batch - 1;
+    prog_mulmod<NT>(buf, mc, a + g * l, b + g * l, out + g * l, store);
+  }
+}
+
+// ---- powmod.  consts = [ blob ].  exp rows in global memory (exp_stride = 0: one shared exponent).
+// nwin_fixed >= 0: uniform window count given by the host; < 0: per element from the bit length
+// (made warp-uniform on the device so that a warp never diverges in the ladder).
+template <int NT, int W>
+PAI_DEV void cta_powmod(u4* smem, const CtaId& id, const uint32_t* base, int base_tiles, const uint32_t* exp, int exp_limbs,
+                        long exp_stride, int nwin_fixed, uint32_t* out, long batch, u4* tbl) {
+  ModC mc;
+  modc_bind(mc, smem, NT);
+  PowEnv<NT> E;
+  cta_bufs<NT>(E.buf, 3, smem, mc_limbs(NT) / 4, id);
+  E.tbl = cta_table<NT, W>(tbl, id);
+  E.mc = &mc;
+  const int l = 8 * NT;
+  for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
+    long g = chunk * id.nthr + id.tid;
+    bool store = g < batch;
+    if (!store) g = batch - 1;
+    const uint32_t* e = exp + g * exp_stride;
+    int nwin = nwin_fixed;
+    if (nwin < 0) {
+      nwin = (limbs_bitlen(e, exp_limbs) + W - 1) / W;
+#if !defined(PAI_HOSTSIM)
+      nwin = __reduce_max_sync(0xffffffffu, nwin);
+#endif
+    }
+    prog_powmod<NT, W>(E, base + g * (long)(8 * base_tiles), base_tiles, e, exp_limbs, nwin, out + g * l, store);
+  }
+}
+
+// ---- invert.  consts = [ blob ]; four buffers.  flags (optional): 0 -> plain copy of a.
+template <int NT>
+PAI_DEV void cta_invert(u4* smem, const CtaId& id, const uint32_t* a, int a_tiles, const int32_t* flags, uint32_t* out,
+                        int32_t* status, long batch) {
+  ModC mc;
+  modc_bind(mc, smem, NT);
+  Opnd buf[4];
+  cta_bufs<NT>(buf, 4, smem, mc_limbs(NT) / 4, id);
+  const int l = 8 * NT;
+  for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
+    long g = chunk * id.nthr + id.tid;
+    if (g >= batch) continue;
+    if (flags && !flags[g]) {
+      const u4* src = (const u4*)(a + g * (long)(8 * a_tiles));
+      u4* dst = (u4*)(out + g * l);
+      u4 z; z.x = z.y = z.z = z.w = 0;
+      for (int q = 0; q < 2 * NT; q++) dst[q] = q < 2 * a_tiles ? src[q] : z;
+      if (status) status[g] = 0;
+      continue;
+    }
+    int fail = prog_invert<NT>(buf, mc, a + g * (long)(8 * a_tiles), a_tiles, out + g * l, true);
+    if (status) status[g] = fail;
+  }
+}
+
+// ---- raw_mul preparation (phe/paillier.py:742-749): s >= n - max_int  ->  flag, exponent n - s
+// Plain one-thread-per-element kernel body over global memory (a few hundred integer ops per element).
+//   n, thresh (= n - max_int): ln limbs.
+PAI_DEV void rawmul_prep(const uint32_t* n, const uint32_t* thresh, int ln, const uint32_t* s, uint32_t* e_out,
+                         int32_t* flag, long g) {
+  const uint32_t* sr = s + g * ln;
+  uint32_t* eo = e_out + g * ln;
+  uint32_t bo = 0;
+  for (int i = 0; i < ln; i++) { uint64_t d = (uint64_t)sr[i] - thresh[i] - bo; bo = (uint32_t)(d >> 63); }
+  int neg = bo ? 0 : 1;                                    // s >= thresh
+  flag[g] = neg;
+  if (neg) {
+    uint32_t b2 = 0;
+    for (int i = 0; i < ln; i++) { uint64_t d = (uint64_t)n[i] - sr[i] - b2; eo[i] = (uint32_t)d; b2 = (uint32_t)(d >> 63); }
+  } else {
+    for (int i = 0; i < ln; i++) eo[i] = sr[i];
+  }
+}
+
+// ---- decrypt.  consts = [ P side | Q side | pinvqM ], side = [ blob(x^2) | blob(x) | xinv | hM | e ]
+template <int NTP>
+PAI_DEV int side_quads() { return mc_limbs(2 * NTP) / 4 + mc_limbs(NTP) / 4 + 3 * 2 * NTP; }
+template <int NTP>
+PAI_DEV int dec_const_quads() { return 2 * side_quads<NTP>() + 2 * NTP; }
+
+template <int NTP>
+PAI_DEV void side_bind(SideC<NTP>& S, u4* base, int nwin) {
+  modc_bind(S.sq, base, 2 * NTP);
+  u4* p = base + mc_limbs(2 * NTP) / 4;
+  modc_bind(S.pr, p, NTP);
+  p += mc_limbs(NTP) / 4;
+  S.xinv.p = p; S.xinv.s = 1;
+  p += 2 * NTP;
+  S.hM.p = p; S.hM.s = 1;
+  p += 2 * NTP;
+  S.e = (const uint32_t*)p;
+  S.nwin = nwin;
+}
+
+template <int NTP, int W>
+PAI_DEV void cta_decrypt(u4* smem, const CtaId& id, int nwin_p, int nwin_q, const uint32_t* c, uint32_t* out, long batch, u4* tbl) {
+  SideC<NTP> P, Qs;
+  side_bind<NTP>(P, smem, nwin_p);
+  side_bind<NTP>(Qs, smem + side_quads<NTP>(), nwin_q);
+  Opnd pinvqM{smem + 2 * side_quads<NTP>(), 1};
+  PowEnv<2 * NTP> E;
+  cta_bufs<2 * NTP>(E.buf, 3, smem, dec_const_quads<NTP>(), id);
+  E.tbl = cta_table<2 * NTP, W>(tbl, id);
+  E.mc = &P.sq;
+  const int lc = 32 * NTP, ln = 16 * NTP;
+  for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
+    long g = chunk * id.nthr + id.tid;
+    bool store = g < batch;
+    if (!store) g = batch - 1;
+    prog_decrypt<NTP, W>(E, P, Qs, pinvqM, c + g * lc, out + g * ln, store);
+  }
+}
+
+}  // namespace pai

@@ -1,0 +1,759 @@
+// pai_engine.cu -- host orchestration + C ABI of libpaillier_b200.so (see include/paillier_b200.h).
+//
+// Product build:   nvcc -gencode arch=compute_100a,code=sm_100a ... -shared  (python-paillier_b200/build.py)
+// Test-only build: g++ -x c++ -DPAI_HOSTSIM ...  -> tests/hostsim/libpaillier_b200_hostsim.so
+//                  (same orchestration, kernels run on the CPU; never loaded by the product package)
+//
+// All big-integer work happens in the kernels (pai_cta.cuh / pai_kernels.cuh / pai_core.cuh).  The
+// host side only pads limb arrays, multiplies p*q / n*n once per key (schoolbook, a few thousand
+// word operations), sizes launches and workspaces, and sequences kernels on the caller's stream.
+#include "pai_rt.h"
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+
+using namespace pai;
+
+// ------------------------------------------------------------------------------------------------
+// kernel bodies (functors launched through rt_launch / k_body)
+namespace {
+
+template <int NT>
+struct SetupBody {
+  const uint32_t* consts; int const_quads;
+  uint32_t* blob; uint32_t* scratch;
+  PAI_MEM void run(u4*, const CtaId& id) const { if (id.tid == 0 && id.cta == 0) mod_setup<NT>(blob, scratch); }
+};
+// x^-1 mod 2^(32 nl) for the L function (single thread)
+struct XinvBody {
+  const uint32_t* consts; int const_quads;
+  uint32_t* out; const uint32_t* x; int nl;
+  PAI_MEM void run(u4*, const CtaId& id) const { if (id.tid == 0 && id.cta == 0) inv_mod_2k(out, x, nl); }
+};
+template <int NT, int W>
+struct EncBody {
+  const uint32_t* consts; int const_quads;
+  int nwin; const uint32_t* m; const uint32_t* r; uint32_t* out; long batch; u4* tbl;
+  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_encrypt<NT, W>(smem, id, nwin, m, r, out, batch, tbl); }
+};
+template <int NT>
+struct MulBody {
+  const uint32_t* consts; int const_quads;
+  const uint32_t* a; const uint32_t* b; uint32_t* out; long batch;
+  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_mulmod<NT>(smem, id, a, b, out, batch); }
+};
+template <int NT, int W>
+struct PowBody {
+  const uint32_t* consts; int const_quads;
+  const uint32_t* base; int base_tiles; const uint32_t* exp; int exp_limbs; long exp_stride; int nwin_fixed;
+  uint32_t* out; long batch; u4* tbl;
+  PAI_MEM void run(u4* smem, const CtaId& id) const {
+    cta_powmod<NT, W>(smem, id, base, base_tiles, exp, exp_limbs, exp_stride, nwin_fixed, out, batch, tbl);
+  }
+};
+template <int NT>
+struct InvBody {
+  const uint32_t* consts; int const_quads;
+  const uint32_t* a; int a_tiles; const int32_t* flags; uint32_t* out; int32_t* status; long batch;
+  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_invert<NT>(smem, id, a, a_tiles, flags, out, status, batch); }
+};
+struct PrepBody {
+  const uint32_t* consts; int const_quads;
+  const uint32_t* n; const uint32_t* thresh; int ln; const uint32_t* s; uint32_t* e_out; int32_t* flag; long batch;
+  PAI_MEM void run(u4*, const CtaId& id) const {
+    for (long g = (long)id.cta * id.nthr + id.tid; g < batch; g += (long)id.ncta * id.nthr) rawmul_prep(n, thresh, ln, s, e_out, flag, g);
+  }
+};
+template <int NTP, int W>
+struct DecBody {
+  const uint32_t* consts; int const_quads;
+  int nwin_p, nwin_q; const uint32_t* c; uint32_t* out; long batch; u4* tbl;
+  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_decrypt<NTP, W>(smem, id, nwin_p, nwin_q, c, out, batch, tbl); }
+};
+// one CRT half with h = 1 (used once per key to derive hp / hq): out = L(g^(x-1) mod x^2) mod x
+template <int NTP, int W>
+struct LBody {
+  const uint32_t* consts; int const_quads;   // one side: [ blob(x^2) | blob(x) | xinv | hM | e ]
+  int nwin; const uint32_t* c; uint32_t* out; u4* tbl;
+  PAI_MEM void run(u4* smem, const CtaId& id) const {
+    if (id.cta != 0 || id.tid != 0) return;
+    SideC<NTP> S;
+    side_bind<NTP>(S, smem, nwin);
+    PowEnv<2 * NTP> E;
+    cta_bufs<2 * NTP>(E.buf, 3, smem, side_quads<NTP>(), id);
+    E.tbl = cta_table<2 * NTP, W>(tbl, id);
+    E.mc = &S.sq;
+    int r = decrypt_half<NTP, W>(E, S, c);
+    store_row(out, E.buf[r], 2 * NTP);
+  }
+};
+
+const int W_ENC = 5, W_DEC = 5, W_VAR = 4;
+const int NTHR_MAX = 128;
+
+int pick_nt(int tiles_needed) {
+  static const int sup[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
+  for (int v : sup) if (v >= tiles_needed) return v;
+  return -1;
+}
+int pick_ntp(int tiles_needed) {
+  static const int sup[] = {1, 2, 3, 4, 6, 8};
+  for (int v : sup) if (v >= tiles_needed) return v;
+  return -1;
+}
+
+// little host helpers on limb vectors (per-key setup only)
+typedef std::vector<uint32_t> limbs_t;
+int eff_limbs(const uint32_t* a, int n) { while (n > 0 && a[n - 1] == 0) n--; return n; }
+int bit_length(const limbs_t& a) {
+  int n = eff_limbs(a.data(), (int)a.size());
+  if (!n) return 0;
+  uint32_t v = a[n - 1]; int b = 0; while (v) { b++; v >>= 1; }
+  return 32 * (n - 1) + b;
+}
+limbs_t h_mul(const limbs_t& a, const limbs_t& b) {
+  limbs_t r(a.size() + b.size(), 0);
+  for (size_t i = 0; i < a.size(); i++) {
+    uint64_t c = 0;
+    for (size_t j = 0; j < b.size(); j++) { uint64_t t = (uint64_t)a[i] * b[j] + r[i + j] + c; r[i + j] = (uint32_t)t; c = t >> 32; }
+    r[i + b.size()] = (uint32_t)c;
+  }
+  return r;
+}
+limbs_t h_sub_small(const limbs_t& a, uint32_t s) {
+  limbs_t r(a); uint64_t bo = s;
+  for (size_t i = 0; i < r.size() && bo; i++) { uint64_t d = (uint64_t)r[i] - bo; r[i] = (uint32_t)d; bo = (d >> 63) & 1; }
+  return r;
+}
+limbs_t h_add_small(const limbs_t& a, uint32_t s) {
+  limbs_t r(a); uint64_t c = s;
+  for (size_t i = 0; i < r.size() && c; i++) { uint64_t d = (uint64_t)r[i] + c; r[i] = (uint32_t)d; c = d >> 32; }
+  return r;
+}
+limbs_t h_div_small(const limbs_t& a, uint32_t d) {
+  limbs_t q(a.size(), 0); uint64_t rem = 0;
+  for (int i = (int)a.size() - 1; i >= 0; i--) { uint64_t t = (rem << 32) | a[i]; q[i] = (uint32_t)(t / d); rem = t % d; }
+  return q;
+}
+limbs_t h_sub(const limbs_t& a, const limbs_t& b) {
+  limbs_t r(a.size()); uint64_t bo = 0;
+  for (size_t i = 0; i < a.size(); i++) { uint64_t d = (uint64_t)a[i] - (i < b.size() ? b[i] : 0) - bo; r[i] = (uint32_t)d; bo = (d >> 63) & 1; }
+  return r;
+}
+int h_cmp(const uint32_t* a, const uint32_t* b, int n) {
+  for (int i = n - 1; i >= 0; i--) if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+  return 0;
+}
+limbs_t padded(const uint32_t* a, int n, int total) {
+  limbs_t r(total, 0);
+  for (int i = 0; i < n && i < total; i++) r[i] = a[i];
+  return r;
+}
+
+struct DevBuf {
+  void* p = nullptr; size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return 0;
+    rt_free(p); p = nullptr; bytes = 0;
+    int rc = rt_malloc(&p, need);
+    if (rc) return rc;
+    bytes = need;
+    return 0;
+  }
+  void release() { rt_free(p); p = nullptr; bytes = 0; }
+};
+
+// launch geometry for a body with `nbuf` operand buffers of NT tiles
+struct Geom { int nthr, grid; size_t smem; };
+template <class Body>
+int geometry(int device, int NT, int const_quads, int nbuf, long batch, Geom& g) {
+  size_t max_smem = rt_max_smem(device);
+  int nthr = NTHR_MAX;
+  size_t smem;
+  for (;;) {
+    smem = ((size_t)const_quads + (size_t)nbuf * 2 * NT * nthr) * 16;
+    if (smem <= max_smem || nthr <= 32) break;
+    nthr -= 32;
+  }
+  if (smem > max_smem) { g_err = "operand size does not fit shared memory"; return PAI_E_ARG; }
+  int occ = rt_occupancy<Body>(nthr, smem);
+  if (occ <= 0) { g_err = "kernel cannot be resident (occupancy 0)"; return PAI_E_CUDA; }
+  long chunks = (batch + nthr - 1) / nthr;
+  long maxgrid = (long)rt_sm_count(device) * occ;
+  g.nthr = nthr; g.smem = smem; g.grid = (int)std::max(1L, std::min(chunks, maxgrid));
+  return 0;
+}
+size_t table_bytes(const Geom& g, int NT, int W) { return (size_t)g.grid * ((size_t)1 << W) * 2 * NT * g.nthr * 16; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+struct pai_mod {
+  int device = 0, NT = 0, L = 0;
+  uint32_t* d_blob = nullptr;       // mc_limbs(NT) (+ extra room requested by the owner)
+  limbs_t h_N;                      // padded modulus
+  DevBuf tbl, tmp_a, tmp_b, tmp_o, tmp_s, tmp_e;
+};
+struct pai_pub {
+  pai_mod* nsq = nullptr;           // modulus n^2; its blob is followed by n (4*NT limbs) for encrypt
+  int ln = 0;                       // limbs of n (= 4*NT)
+  uint32_t* d_nth = nullptr;        // [ n | n - max_int ]  (ln limbs each) for raw_mul's branch test
+  DevBuf w_base, w_exp, w_flag, h_m, h_r, h_c, h_s;
+  limbs_t h_n;
+};
+struct pai_priv {
+  int device = 0, NTP = 0;
+  pai_mod *p2 = nullptr, *q2 = nullptr, *p1 = nullptr, *q1 = nullptr;
+  uint32_t* d_consts = nullptr;     // [ P side | Q side | pinvqM ]
+  int nwin_p = 0, nwin_q = 0;
+  limbs_t h_p, h_q, h_pinv, h_hp, h_hq;   // 16*NTP limbs each (padded)
+  DevBuf tbl, h_c, h_m;
+};
+
+// ------------------------------------------------------------------------------------------------
+#define DISPATCH_NT(NTV, CALL)                                                                        \
+  switch (NTV) {                                                                                      \
+    case 1: { constexpr int NT = 1; CALL; } break;                                                    \
+    case 2: { constexpr int NT = 2; CALL; } break;                                                    \
+    case 3: { constexpr int NT = 3; CALL; } break;                                                    \
+    case 4: { constexpr int NT = 4; CALL; } break;                                                    \
+    case 6: { constexpr int NT = 6; CALL; } break;                                                    \
+    case 8: { constexpr int NT = 8; CALL; } break;                                                    \
+    case 12: { constexpr int NT = 12; CALL; } break;                                                  \
+    case 16: { constexpr int NT = 16; CALL; } break;                                                  \
+    case 24: { constexpr int NT = 24; CALL; } break;                                                  \
+    case 32: { constexpr int NT = 32; CALL; } break;                                                  \
+    default: g_err = "unsupported operand size"; rc = PAI_E_ARG;                                      \
+  }
+#define DISPATCH_NTP(NTV, CALL)                                                                       \
+  switch (NTV) {                                                                                      \
+    case 1: { constexpr int NTP = 1; CALL; } break;                                                   \
+    case 2: { constexpr int NTP = 2; CALL; } break;                                                   \
+    case 3: { constexpr int NTP = 3; CALL; } break;                                                   \
+    case 4: { constexpr int NTP = 4; CALL; } break;                                                   \
+    case 6: { constexpr int NTP = 6; CALL; } break;                                                   \
+    case 8: { constexpr int NTP = 8; CALL; } break;                                                   \
+    default: g_err = "unsupported key size"; rc = PAI_E_ARG;                                          \
+  }
+
+namespace {
+
+template <int NT>
+int do_setup(pai_mod* m, rt_stream s) {
+  void* scratch = nullptr;
+  int rc = rt_malloc(&scratch, (size_t)3 * 8 * NT * 4);
+  if (rc) return rc;
+  SetupBody<NT> b{nullptr, 0, m->d_blob, (uint32_t*)scratch};
+  rc = rt_launch(b, 1, 32, 0, s);
+  if (!rc) rc = rt_sync(s);
+  rt_free(scratch);
+  return rc;
+}
+
+// create a modulus context; extra_limbs of device room are left after the blob
+int mod_create_impl(const uint32_t* modulus, int limbs, int device, int force_nt, int extra_limbs, pai_mod** out) {
+  if (!modulus || !out || limbs <= 0) { g_err = "null/empty modulus"; return PAI_E_ARG; }
+  int eff = eff_limbs(modulus, limbs);
+  if (eff == 0 || !(modulus[0] & 1u)) { g_err = "modulus must be odd and non-zero"; return PAI_E_ARG; }
+  if (eff == 1 && modulus[0] == 1u) { g_err = "modulus must be > 1"; return PAI_E_ARG; }
+  int NT = force_nt > 0 ? force_nt : pick_nt((eff + 7) / 8);
+  if (NT < 0 || 8 * NT < eff) { g_err = "modulus too large (max 8192 bits)"; return PAI_E_ARG; }
+  if (rt_device_count() <= device) { g_err = "no such CUDA device (this engine has no CPU fallback)"; return PAI_E_CUDA; }
+  int rc = rt_set_device(device);
+  if (rc) return rc;
+  pai_mod* m = new (std::nothrow) pai_mod();
+  if (!m) return PAI_E_ARG;
+  m->device = device; m->NT = NT; m->L = 8 * NT;
+  m->h_N = padded(modulus, eff, m->L);
+  rc = rt_malloc((void**)&m->d_blob, ((size_t)mc_limbs(NT) + extra_limbs) * 4);
+  if (!rc) rc = rt_memset(m->d_blob, 0, ((size_t)mc_limbs(NT) + extra_limbs) * 4, 0);
+  if (!rc) rc = rt_h2d(m->d_blob, m->h_N.data(), (size_t)m->L * 4, 0);
+  if (!rc) { DISPATCH_NT(NT, rc = do_setup<NT>(m, 0)); }
+  if (rc) { rt_free(m->d_blob); delete m; return rc; }
+  *out = m;
+  return 0;
+}
+void mod_free(pai_mod* m) {
+  if (!m) return;
+  rt_set_device(m->device);
+  rt_free(m->d_blob);
+  m->tbl.release(); m->tmp_a.release(); m->tmp_b.release(); m->tmp_o.release(); m->tmp_s.release(); m->tmp_e.release();
+  delete m;
+}
+
+template <int NT>
+int do_mulmod(pai_mod* m, const uint32_t* consts, int cq, const uint32_t* a, const uint32_t* b, uint32_t* out, long batch, rt_stream s) {
+  typedef MulBody<NT> B;
+  Geom g;
+  int rc = geometry<B>(m->device, NT, cq, 3, batch, g);
+  if (rc) return rc;
+  B body{consts, cq, a, b, out, batch};
+  return rt_launch(body, g.grid, g.nthr, g.smem, s);
+}
+
+template <int NT>
+int do_powmod(pai_mod* m, const uint32_t* base, int base_tiles, const uint32_t* d_exp, int exp_limbs, long exp_stride,
+              int nwin_fixed, uint32_t* out, long batch, rt_stream s) {
+  typedef PowBody<NT, W_VAR> B;
+  Geom g;
+  int cq = mc_limbs(NT) / 4;
+  int rc = geometry<B>(m->device, NT, cq, 3, batch, g);
+  if (rc) return rc;
+  rc = m->tbl.ensure(table_bytes(g, NT, W_VAR));
+  if (rc) return rc;
+  B body{m->d_blob, cq, base, base_tiles, d_exp, exp_limbs, exp_stride, nwin_fixed, out, batch, (u4*)m->tbl.p};
+  return rt_launch(body, g.grid, g.nthr, g.smem, s);
+}
+
+template <int NT>
+int do_invert(pai_mod* m, const uint32_t* a, int a_tiles, const int32_t* flags, uint32_t* out, int32_t* status, long batch, rt_stream s) {
+  typedef InvBody<NT> B;
+  Geom g;
+  int cq = mc_limbs(NT) / 4;
+  int rc = geometry<B>(m->device, NT, cq, 4, batch, g);
+  if (rc) return rc;
+  B body{m->d_blob, cq, a, a_tiles, flags, out, status, batch};
+  return rt_launch(body, g.grid, g.nthr, g.smem, s);
+}
+
+template <int NT>
+int do_encrypt(pai_pub* k, const uint32_t* m_, const uint32_t* r, uint32_t* c, long batch, rt_stream s) {
+  typedef EncBody<NT, W_ENC> B;
+  pai_mod* m = k->nsq;
+  Geom g;
+  int cq = mc_limbs(NT) / 4 + NT;
+  int rc = geometry<B>(m->device, NT, cq, 3, batch, g);
+  if (rc) return rc;
+  rc = m->tbl.ensure(table_bytes(g, NT, W_ENC));
+  if (rc) return rc;
+  int nwin = (bit_length(k->h_n) + W_ENC - 1) / W_ENC;
+  B body{m->d_blob, cq, nwin, m_, r, c, batch, (u4*)m->tbl.p};
+  return rt_launch(body, g.grid, g.nthr, g.smem, s);
+}
+
+template <int NTP>
+int do_decrypt(pai_priv* k, const uint32_t* c, uint32_t* out, long batch, rt_stream s) {
+  typedef DecBody<NTP, W_DEC> B;
+  Geom g;
+  int cq = 2 * (mc_limbs(2 * NTP) / 4 + mc_limbs(NTP) / 4 + 6 * NTP) + 2 * NTP;
+  int rc = geometry<B>(k->device, 2 * NTP, cq, 3, batch, g);
+  if (rc) return rc;
+  rc = k->tbl.ensure(table_bytes(g, 2 * NTP, W_DEC));
+  if (rc) return rc;
+  B body{k->d_consts, cq, k->nwin_p, k->nwin_q, c, out, batch, (u4*)k->tbl.p};
+  return rt_launch(body, g.grid, g.nthr, g.smem, s);
+}
+
+// derive one side's constants on the device.  side layout: [ blob(x^2) | blob(x) | xinv | hM | e ]
+template <int NTP>
+int do_side(pai_priv* k, pai_mod* m2, pai_mod* m1, const limbs_t& x, const limbs_t& g_pad, uint32_t* d_side, int nwin,
+            limbs_t& h_out, rt_stream s) {
+  const int NT2 = 2 * NTP, L1 = 8 * NTP;
+  uint32_t* d_b2 = d_side;
+  uint32_t* d_b1 = d_b2 + mc_limbs(NT2);
+  uint32_t* d_xinv = d_b1 + mc_limbs(NTP);
+  uint32_t* d_hM = d_xinv + L1;
+  uint32_t* d_e = d_hM + L1;
+  int rc = rt_d2d(d_b2, m2->d_blob, (size_t)mc_limbs(NT2) * 4, s);
+  if (!rc) rc = rt_d2d(d_b1, m1->d_blob, (size_t)mc_limbs(NTP) * 4, s);
+  // x^-1 mod 2^(256 NTP)
+  if (!rc) { XinvBody xb{nullptr, 0, d_xinv, d_b1 /* N of blob(x) */, L1}; rc = rt_launch(xb, 1, 32, 0, s); }
+  // exponent x - 1
+  limbs_t e = h_sub_small(x, 1);
+  if (!rc) rc = rt_h2d(d_e, e.data(), (size_t)L1 * 4, s);
+  // h = 1 for now: hM = R1 of blob(x)
+  if (!rc) rc = rt_d2d(d_hM, d_b1 + L1, (size_t)L1 * 4, s);
+  if (rc) return rc;
+  // l = L(g^(x-1) mod x^2) mod x  via one CRT half with h = 1 on the "ciphertext" g = n + 1
+  void *d_g = nullptr, *d_l = nullptr, *d_h = nullptr, *d_st = nullptr, *d_hm = nullptr;
+  rc = rt_malloc(&d_g, (size_t)2 * 8 * NT2 * 4);
+  if (!rc) rc = rt_malloc(&d_l, (size_t)L1 * 4);
+  if (!rc) rc = rt_malloc(&d_h, (size_t)L1 * 4);
+  if (!rc) rc = rt_malloc(&d_hm, (size_t)L1 * 4);
+  if (!rc) rc = rt_malloc(&d_st, 16);
+  if (!rc) rc = rt_h2d(d_g, g_pad.data(), (size_t)2 * 8 * NT2 * 4, s);
+  if (!rc) {
+    typedef LBody<NTP, W_DEC> B;
+    int cq = mc_limbs(NT2) / 4 + mc_limbs(NTP) / 4 + 6 * NTP;
+    Geom g;
+    rc = geometry<B>(k->device, NT2, cq, 3, 1, g);
+    if (!rc) rc = k->tbl.ensure(table_bytes(g, NT2, W_DEC));
+    if (!rc) { B body{d_side, cq, nwin, (const uint32_t*)d_g, (uint32_t*)d_l, (u4*)k->tbl.p}; rc = rt_launch(body, 1, g.nthr, g.smem, s); }
+  }
+  // h = l^-1 mod x  (phe/paillier.py:360), then hM = h * R mod x
+  if (!rc) rc = do_invert<NTP>(m1, (const uint32_t*)d_l, NTP, nullptr, (uint32_t*)d_h, (int32_t*)d_st, 1, s);
+  int32_t st = 0;
+  if (!rc) rc = rt_d2h(&st, d_st, 4, s);
+  if (!rc) rc = rt_sync(s);
+  if (!rc && st) { g_err = "h_function: inverse does not exist"; rc = PAI_E_NOINV; }
+  if (!rc) rc = do_mulmod<NTP>(m1, m1->d_blob, mc_limbs(NTP) / 4, (const uint32_t*)d_h, m1->d_blob + L1 /* R1 as a plain number */,
+                               (uint32_t*)d_hm, 1, s);
+  if (!rc) rc = rt_d2d(d_hM, d_hm, (size_t)L1 * 4, s);
+  h_out.assign(L1, 0);
+  if (!rc) rc = rt_d2h(h_out.data(), d_h, (size_t)L1 * 4, s);
+  if (!rc) rc = rt_sync(s);
+  rt_free(d_g); rt_free(d_l); rt_free(d_h); rt_free(d_hm); rt_free(d_st);
+  return rc;
+}
+
+template <int NTP>
+int do_priv_setup(pai_priv* k, rt_stream s) {
+  const int L1 = 8 * NTP, NT2 = 2 * NTP;
+  const int sideq = mc_limbs(NT2) / 4 + mc_limbs(NTP) / 4 + 6 * NTP;
+  size_t total = ((size_t)2 * sideq + 2 * NTP) * 16;
+  int rc = rt_malloc((void**)&k->d_consts, total);
+  if (!rc) rc = rt_memset(k->d_consts, 0, total, s);
+  if (rc) return rc;
+  limbs_t p = padded(k->h_p.data(), L1, L1), q = padded(k->h_q.data(), L1, L1);
+  limbs_t n = h_mul(p, q);                         // 2*L1 limbs
+  limbs_t g = h_add_small(n, 1);                   // g = n + 1 (phe/paillier.py:87); cannot overflow 2*L1 limbs for n = p*q odd < 2^k - 1
+  limbs_t g_pad = padded(g.data(), (int)g.size(), 2 * 8 * NT2);
+  k->nwin_p = (bit_length(h_sub_small(p, 1)) + W_DEC - 1) / W_DEC;
+  k->nwin_q = (bit_length(h_sub_small(q, 1)) + W_DEC - 1) / W_DEC;
+  uint32_t* d_P = k->d_consts;
+  uint32_t* d_Q = k->d_consts + (size_t)sideq * 4;
+  uint32_t* d_pinvqM = k->d_consts + (size_t)2 * sideq * 4;
+  rc = do_side<NTP>(k, k->p2, k->p1, p, g_pad, d_P, k->nwin_p, k->h_hp, s);
+  if (!rc) rc = do_side<NTP>(k, k->q2, k->q1, q, g_pad, d_Q, k->nwin_q, k->h_hq, s);
+  if (rc) return rc;
+  // p_inverse = p^-1 mod q (phe/paillier.py:233); pinvqM = p_inverse * R mod q
+  void *d_p = nullptr, *d_pi = nullptr, *d_st = nullptr, *d_pm = nullptr;
+  rc = rt_malloc(&d_p, (size_t)L1 * 4);
+  if (!rc) rc = rt_malloc(&d_pi, (size_t)L1 * 4);
+  if (!rc) rc = rt_malloc(&d_pm, (size_t)L1 * 4);
+  if (!rc) rc = rt_malloc(&d_st, 16);
+  if (!rc) rc = rt_h2d(d_p, p.data(), (size_t)L1 * 4, s);
+  if (!rc) rc = do_invert<NTP>(k->q1, (const uint32_t*)d_p, NTP, nullptr, (uint32_t*)d_pi, (int32_t*)d_st, 1, s);
+  int32_t st = 0;
+  if (!rc) rc = rt_d2h(&st, d_st, 4, s);
+  if (!rc) rc = rt_sync(s);
+  if (!rc && st) { g_err = "p has no inverse mod q"; rc = PAI_E_NOINV; }
+  if (!rc) rc = do_mulmod<NTP>(k->q1, k->q1->d_blob, mc_limbs(NTP) / 4, (const uint32_t*)d_pi, k->q1->d_blob + L1, (uint32_t*)d_pm, 1, s);
+  if (!rc) rc = rt_d2d(d_pinvqM, d_pm, (size_t)L1 * 4, s);
+  k->h_pinv.assign(L1, 0);
+  if (!rc) rc = rt_d2h(k->h_pinv.data(), d_pi, (size_t)L1 * 4, s);
+  if (!rc) rc = rt_sync(s);
+  rt_free(d_p); rt_free(d_pi); rt_free(d_pm); rt_free(d_st);
+  return rc;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* pai_last_error(void) { return g_err.c_str(); }
+int pai_version(void) { return 100; }
+int pai_device_count(void) { return rt_device_count(); }
+long pai_launch_count(void) { return g_launches.load(); }
+
+int pai_mod_create(const uint32_t* modulus, int limbs, int device, pai_mod** out) {
+  return mod_create_impl(modulus, limbs, device, 0, 0, out);
+}
+int pai_mod_destroy(pai_mod* m) { mod_free(m); return 0; }
+int pai_mod_limbs(const pai_mod* m) { return m ? m->L : PAI_E_ARG; }
+
+int pai_mod_mulmod(pai_mod* m, const uint32_t* d_a, const uint32_t* d_b, uint32_t* d_out, long batch, void* stream) {
+  if (!m || !d_a || !d_b || !d_out || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  if (batch == 0) return 0;
+  int rc = rt_set_device(m->device);
+  if (rc) return rc;
+  DISPATCH_NT(m->NT, rc = do_mulmod<NT>(m, m->d_blob, mc_limbs(NT) / 4, d_a, d_b, d_out, batch, (rt_stream)stream));
+  return rc;
+}
+
+static int powmod_common(pai_mod* m, const uint32_t* d_base, int base_limbs, const uint32_t* d_exp, int exp_limbs, long exp_stride,
+                         int nwin_fixed, uint32_t* d_out, long batch, void* stream) {
+  if (base_limbs != m->L && base_limbs != 2 * m->L) { g_err = "base_limbs must be L or 2L"; return PAI_E_ARG; }
+  int rc = 0;
+  DISPATCH_NT(m->NT, rc = do_powmod<NT>(m, d_base, base_limbs / 8, d_exp, exp_limbs, exp_stride, nwin_fixed, d_out, batch, (rt_stream)stream));
+  return rc;
+}
+
+int pai_mod_powmod_shared(pai_mod* m, const uint32_t* d_base, int base_limbs, const uint32_t* exponent, int exp_limbs,
+                          uint32_t* d_out, long batch, void* stream) {
+  if (!m || !d_base || !exponent || !d_out || batch < 0 || exp_limbs <= 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  if (batch == 0) return 0;
+  int rc = rt_set_device(m->device);
+  if (rc) return rc;
+  limbs_t e(exponent, exponent + exp_limbs);
+  int nwin = (bit_length(e) + W_VAR - 1) / W_VAR;
+  rc = m->tmp_e.ensure((size_t)exp_limbs * 4);
+  if (!rc) rc = rt_h2d(m->tmp_e.p, exponent, (size_t)exp_limbs * 4, (rt_stream)stream);
+  if (!rc) rc = rt_sync((rt_stream)stream);   // `exponent` is caller-owned host memory
+  if (rc) return rc;
+  return powmod_common(m, d_base, base_limbs, (const uint32_t*)m->tmp_e.p, exp_limbs, 0, nwin, d_out, batch, stream);
+}
+
+int pai_mod_powmod(pai_mod* m, const uint32_t* d_base, int base_limbs, const uint32_t* d_exp, int exp_limbs,
+                   uint32_t* d_out, long batch, void* stream) {
+  if (!m || !d_base || !d_exp || !d_out || batch < 0 || exp_limbs <= 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  if (batch == 0) return 0;
+  int rc = rt_set_device(m->device);
+  if (rc) return rc;
+  return powmod_common(m, d_base, base_limbs, d_exp, exp_limbs, exp_limbs, -1, d_out, batch, stream);
+}
+
+int pai_mod_invert(pai_mod* m, const uint32_t* d_a, int a_limbs, uint32_t* d_out, int32_t* d_status, long batch, void* stream) {
+  if (!m || !d_a || !d_out || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  if (a_limbs != m->L) { g_err = "a_limbs must equal pai_mod_limbs()"; return PAI_E_ARG; }
+  if (batch == 0) return 0;
+  int rc = rt_set_device(m->device);
+  if (rc) return rc;
+  DISPATCH_NT(m->NT, rc = do_invert<NT>(m, d_a, a_limbs / 8, nullptr, d_out, d_status, batch, (rt_stream)stream));
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------- public key
+int pai_pub_create(const uint32_t* n, int limbs, int device, pai_pub** out) {
+  if (!n || !out || limbs <= 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  int eff = eff_limbs(n, limbs);
+  if (eff == 0 || !(n[0] & 1u)) { g_err = "n must be odd"; return PAI_E_ARG; }
+  // n has 2*NTp tiles, n^2 4*NTp, where NTp covers half of n's limbs
+  int ntp = pick_ntp((eff + 15) / 16);
+  if (ntp < 0) { g_err = "key too large (max 4096 bits)"; return PAI_E_ARG; }
+  int NT = 4 * ntp, ln = 4 * NT;
+  limbs_t nn = padded(n, eff, ln);
+  limbs_t nsq = h_mul(nn, nn);                     // 2*ln = 8*NT limbs
+  pai_pub* k = new (std::nothrow) pai_pub();
+  if (!k) return PAI_E_ARG;
+  k->ln = ln; k->h_n = nn;
+  int rc = mod_create_impl(nsq.data(), (int)nsq.size(), device, NT, ln, &k->nsq);
+  if (rc) { delete k; return rc; }
+  // n right after the blob (encrypt's constant area)
+  rc = rt_h2d(k->nsq->d_blob + mc_limbs(NT), nn.data(), (size_t)ln * 4, 0);
+  // raw_mul branch threshold n - max_int, max_int = n//3 - 1   (phe/paillier.py:90, 745)
+  limbs_t maxint = h_sub_small(h_div_small(nn, 3), 1);
+  limbs_t thr = h_sub(nn, maxint);
+  if (!rc) rc = rt_malloc((void**)&k->d_nth, (size_t)2 * ln * 4);
+  if (!rc) rc = rt_h2d(k->d_nth, nn.data(), (size_t)ln * 4, 0);
+  if (!rc) rc = rt_h2d(k->d_nth + ln, thr.data(), (size_t)ln * 4, 0);
+  if (!rc) rc = rt_sync(0);
+  if (rc) { pai_pub_destroy(k); return rc; }
+  *out = k;
+  return 0;
+}
+int pai_pub_destroy(pai_pub* k) {
+  if (!k) return 0;
+  if (k->nsq) rt_set_device(k->nsq->device);
+  rt_free(k->d_nth);
+  k->w_base.release(); k->w_exp.release(); k->w_flag.release(); k->h_m.release(); k->h_r.release(); k->h_c.release(); k->h_s.release();
+  mod_free(k->nsq);
+  delete k;
+  return 0;
+}
+int pai_pub_n_limbs(const pai_pub* k) { return k ? k->ln : PAI_E_ARG; }
+int pai_pub_c_limbs(const pai_pub* k) { return k ? 2 * k->ln : PAI_E_ARG; }
+
+int pai_encrypt(pai_pub* k, const uint32_t* d_m, const uint32_t* d_r, uint32_t* d_c, long batch, void* stream) {
+  if (!k || !d_m || !d_r || !d_c || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  if (batch == 0) return 0;
+  int rc = rt_set_device(k->nsq->device);
+  if (rc) return rc;
+  DISPATCH_NT(k->nsq->NT, rc = do_encrypt<NT>(k, d_m, d_r, d_c, batch, (rt_stream)stream));
+  return rc;
+}
+int pai_raw_add(pai_pub* k, const uint32_t* d_a, const uint32_t* d_b, uint32_t* d_c, long batch, void* stream) {
+  if (!k) { g_err = "bad argument"; return PAI_E_ARG; }
+  return pai_mod_mulmod(k->nsq, d_a, d_b, d_c, batch, stream);
+}
+int pai_raw_mul(pai_pub* k, const uint32_t* d_a, const uint32_t* d_s, uint32_t* d_c, int32_t* d_status, long batch, void* stream) {
+  if (!k || !d_a || !d_s || !d_c || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  if (batch == 0) return 0;
+  pai_mod* m = k->nsq;
+  rt_stream s = (rt_stream)stream;
+  int rc = rt_set_device(m->device);
+  const int ln = k->ln, lc = 2 * k->ln;
+  if (!rc) rc = k->w_exp.ensure((size_t)batch * ln * 4);
+  if (!rc) rc = k->w_base.ensure((size_t)batch * lc * 4);
+  if (!rc) rc = k->w_flag.ensure((size_t)batch * 4 * 2);
+  if (rc) return rc;
+  int32_t* flag = (int32_t*)k->w_flag.p;
+  int32_t* status = d_status ? d_status : flag + batch;
+  // 1. branch test + exponent (s or n - s)
+  {
+    PrepBody b{nullptr, 0, k->d_nth, k->d_nth + ln, ln, d_s, (uint32_t*)k->w_exp.p, flag, batch};
+    long blocks = (batch + 127) / 128;
+    rc = rt_launch(b, (int)std::min(blocks, 65535L), 128, 0, s);
+    if (rc) return rc;
+  }
+  // 2. base = a, or invert(a, n^2) where flagged
+  DISPATCH_NT(m->NT, rc = do_invert<NT>(m, d_a, lc / 8, flag, (uint32_t*)k->w_base.p, status, batch, s));
+  if (rc) return rc;
+  // 3. base ^ exponent mod n^2
+  return powmod_common(m, (const uint32_t*)k->w_base.p, lc, (const uint32_t*)k->w_exp.p, ln, ln, -1, d_c, batch, stream);
+}
+
+// ---------------------------------------------------------------------------------------- private key
+int pai_priv_create(const uint32_t* p, const uint32_t* q, int limbs, int device, pai_priv** out) {
+  if (!p || !q || !out || limbs <= 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  int ep = eff_limbs(p, limbs), eq = eff_limbs(q, limbs);
+  if (!ep || !eq || !(p[0] & 1u) || !(q[0] & 1u)) { g_err = "p and q must be odd"; return PAI_E_ARG; }
+  int ntp = pick_ntp((std::max(ep, eq) + 7) / 8);
+  if (ntp < 0) { g_err = "key too large (max 4096 bits)"; return PAI_E_ARG; }
+  const int L1 = 8 * ntp;
+  limbs_t pp = padded(p, ep, L1), qq = padded(q, eq, L1);
+  int c = h_cmp(pp.data(), qq.data(), L1);
+  if (c == 0) { g_err = "p and q have to be different"; return PAI_E_ARG; }     // phe/paillier.py:220-222
+  if (c > 0) std::swap(pp, qq);                                                   // :224-229
+  pai_priv* k = new (std::nothrow) pai_priv();
+  if (!k) return PAI_E_ARG;
+  k->device = device; k->NTP = ntp; k->h_p = pp; k->h_q = qq;
+  limbs_t p2 = h_mul(pp, pp), q2 = h_mul(qq, qq);
+  int rc = mod_create_impl(p2.data(), (int)p2.size(), device, 2 * ntp, 0, &k->p2);
+  if (!rc) rc = mod_create_impl(q2.data(), (int)q2.size(), device, 2 * ntp, 0, &k->q2);
+  if (!rc) rc = mod_create_impl(pp.data(), L1, device, ntp, 0, &k->p1);
+  if (!rc) rc = mod_create_impl(qq.data(), L1, device, ntp, 0, &k->q1);
+  if (!rc) { DISPATCH_NTP(ntp, rc = do_priv_setup<NTP>(k, 0)); }
+  if (rc) { pai_priv_destroy(k); return rc; }
+  *out = k;
+  return 0;
+}
+int pai_priv_destroy(pai_priv* k) {
+  if (!k) return 0;
+  rt_set_device(k->device);
+  if (k->d_consts) {                      // wipe the secret constants before releasing them
+    const int sideq = mc_limbs(2 * k->NTP) / 4 + mc_limbs(k->NTP) / 4 + 6 * k->NTP;
+    rt_memset(k->d_consts, 0, ((size_t)2 * sideq + 2 * k->NTP) * 16, 0);
+    rt_sync(0);
+  }
+  rt_free(k->d_consts);
+  k->tbl.release(); k->h_c.release(); k->h_m.release();
+  mod_free(k->p2); mod_free(k->q2); mod_free(k->p1); mod_free(k->q1);
+  std::fill(k->h_p.begin(), k->h_p.end(), 0); std::fill(k->h_q.begin(), k->h_q.end(), 0);
+  delete k;
+  return 0;
+}
+int pai_priv_n_limbs(const pai_priv* k) { return k ? 16 * k->NTP : PAI_E_ARG; }
+int pai_priv_c_limbs(const pai_priv* k) { return k ? 32 * k->NTP : PAI_E_ARG; }
+int pai_priv_get(const pai_priv* k, uint32_t* p, uint32_t* q, uint32_t* p_inverse, uint32_t* hp, uint32_t* hq) {
+  if (!k) return PAI_E_ARG;
+  const int ln = 16 * k->NTP, L1 = 8 * k->NTP;
+  const limbs_t* src[5] = {&k->h_p, &k->h_q, &k->h_pinv, &k->h_hp, &k->h_hq};
+  uint32_t* dst[5] = {p, q, p_inverse, hp, hq};
+  for (int i = 0; i < 5; i++) {
+    if (!dst[i]) continue;
+    memset(dst[i], 0, (size_t)ln * 4);
+    memcpy(dst[i], src[i]->data(), (size_t)L1 * 4);
+  }
+  return 0;
+}
+int pai_decrypt(pai_priv* k, const uint32_t* d_c, uint32_t* d_m, long batch, void* stream) {
+  if (!k || !d_c || !d_m || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  if (batch == 0) return 0;
+  int rc = rt_set_device(k->device);
+  if (rc) return rc;
+  DISPATCH_NTP(k->NTP, rc = do_decrypt<NTP>(k, d_c, d_m, batch, (rt_stream)stream));
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------- host-pointer variants
+#define STAGE_IN(buf, host, bytes) do { rc = (buf).ensure(bytes); if (!rc) rc = rt_h2d((buf).p, host, bytes, 0); if (rc) return rc; } while (0)
+
+int pai_encrypt_host(pai_pub* k, const uint32_t* m, const uint32_t* r, uint32_t* c, long batch) {
+  if (!k || !m || !r || !c || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  if (batch == 0) return 0;
+  int rc = rt_set_device(k->nsq->device);
+  if (rc) return rc;
+  size_t bn = (size_t)batch * k->ln * 4;
+  STAGE_IN(k->h_m, m, bn);
+  STAGE_IN(k->h_r, r, bn);
+  rc = k->h_c.ensure(2 * bn);
+  if (!rc) rc = pai_encrypt(k, (const uint32_t*)k->h_m.p, (const uint32_t*)k->h_r.p, (uint32_t*)k->h_c.p, batch, nullptr);
+  if (!rc) rc = rt_d2h(c, k->h_c.p, 2 * bn, 0);
+  if (!rc) rc = rt_sync(0);
+  return rc;
+}
+int pai_raw_add_host(pai_pub* k, const uint32_t* a, const uint32_t* b, uint32_t* c, long batch) {
+  if (!k || !a || !b || !c || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  if (batch == 0) return 0;
+  int rc = rt_set_device(k->nsq->device);
+  if (rc) return rc;
+  size_t bc = (size_t)batch * 2 * k->ln * 4;
+  STAGE_IN(k->h_m, a, bc);
+  STAGE_IN(k->h_r, b, bc);
+  rc = k->h_c.ensure(bc);
+  if (!rc) rc = pai_raw_add(k, (const uint32_t*)k->h_m.p, (const uint32_t*)k->h_r.p, (uint32_t*)k->h_c.p, batch, nullptr);
+  if (!rc) rc = rt_d2h(c, k->h_c.p, bc, 0);
+  if (!rc) rc = rt_sync(0);
+  return rc;
+}
+int pai_raw_mul_host(pai_pub* k, const uint32_t* a, const uint32_t* s, uint32_t* c, int32_t* status, long batch) {
+  if (!k || !a || !s || !c || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  if (batch == 0) return 0;
+  int rc = rt_set_device(k->nsq->device);
+  if (rc) return rc;
+  size_t bn = (size_t)batch * k->ln * 4;
+  STAGE_IN(k->h_m, a, 2 * bn);
+  STAGE_IN(k->h_s, s, bn);
+  rc = k->h_c.ensure(2 * bn);
+  if (!rc) rc = k->h_r.ensure((size_t)batch * 4);
+  if (!rc) rc = pai_raw_mul(k, (const uint32_t*)k->h_m.p, (const uint32_t*)k->h_s.p, (uint32_t*)k->h_c.p, (int32_t*)k->h_r.p, batch, nullptr);
+  if (!rc) rc = rt_d2h(c, k->h_c.p, 2 * bn, 0);
+  if (!rc && status) rc = rt_d2h(status, k->h_r.p, (size_t)batch * 4, 0);
+  if (!rc) rc = rt_sync(0);
+  return rc;
+}
+int pai_decrypt_host(pai_priv* k, const uint32_t* c, uint32_t* m, long batch) {
+  if (!k || !c || !m || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  if (batch == 0) return 0;
+  int rc = rt_set_device(k->device);
+  if (rc) return rc;
+  size_t bn = (size_t)batch * 16 * k->NTP * 4;
+  STAGE_IN(k->h_c, c, 2 * bn);
+  rc = k->h_m.ensure(bn);
+  if (!rc) rc = pai_decrypt(k, (const uint32_t*)k->h_c.p, (uint32_t*)k->h_m.p, batch, nullptr);
+  if (!rc) rc = rt_d2h(m, k->h_m.p, bn, 0);
+  if (!rc) rc = rt_sync(0);
+  return rc;
+}
+int pai_mod_mulmod_host(pai_mod* m, const uint32_t* a, const uint32_t* b, uint32_t* out, long batch) {
+  if (!m || !a || !b || !out || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  if (batch == 0) return 0;
+  int rc = rt_set_device(m->device);
+  if (rc) return rc;
+  size_t bl = (size_t)batch * m->L * 4;
+  STAGE_IN(m->tmp_a, a, bl);
+  STAGE_IN(m->tmp_b, b, bl);
+  rc = m->tmp_o.ensure(bl);
+  if (!rc) rc = pai_mod_mulmod(m, (const uint32_t*)m->tmp_a.p, (const uint32_t*)m->tmp_b.p, (uint32_t*)m->tmp_o.p, batch, nullptr);
+  if (!rc) rc = rt_d2h(out, m->tmp_o.p, bl, 0);
+  if (!rc) rc = rt_sync(0);
+  return rc;
+}
+int pai_mod_powmod_host(pai_mod* m, const uint32_t* base, int base_limbs, const uint32_t* exp, int exp_limbs, int shared_exp,
+                        uint32_t* out, long batch) {
+  if (!m || !base || !exp || !out || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  if (batch == 0) return 0;
+  int rc = rt_set_device(m->device);
+  if (rc) return rc;
+  STAGE_IN(m->tmp_a, base, (size_t)batch * base_limbs * 4);
+  rc = m->tmp_o.ensure((size_t)batch * m->L * 4);
+  if (rc) return rc;
+  if (shared_exp) {
+    rc = pai_mod_powmod_shared(m, (const uint32_t*)m->tmp_a.p, base_limbs, exp, exp_limbs, (uint32_t*)m->tmp_o.p, batch, nullptr);
+  } else {
+    STAGE_IN(m->tmp_b, exp, (size_t)batch * exp_limbs * 4);
+    rc = pai_mod_powmod(m, (const uint32_t*)m->tmp_a.p, base_limbs, (const uint32_t*)m->tmp_b.p, exp_limbs, (uint32_t*)m->tmp_o.p, batch, nullptr);
+  }
+  if (!rc) rc = rt_d2h(out, m->tmp_o.p, (size_t)batch * m->L * 4, 0);
+  if (!rc) rc = rt_sync(0);
+  return rc;
+}
+int pai_mod_invert_host(pai_mod* m, const uint32_t* a, int a_limbs, uint32_t* out, int32_t* status, long batch) {
+  if (!m || !a || !out || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  if (batch == 0) return 0;
+  int rc = rt_set_device(m->device);
+  if (rc) return rc;
+  STAGE_IN(m->tmp_a, a, (size_t)batch * a_limbs * 4);
+  rc = m->tmp_o.ensure((size_t)batch * m->L * 4);
+  if (!rc) rc = m->tmp_s.ensure((size_t)batch * 4);
+  if (!rc) rc = pai_mod_invert(m, (const uint32_t*)m->tmp_a.p, a_limbs, (uint32_t*)m->tmp_o.p, (int32_t*)m->tmp_s.p, batch, nullptr);
+  if (!rc) rc = rt_d2h(out, m->tmp_o.p, (size_t)batch * m->L * 4, 0);
+  if (!rc && status) rc = rt_d2h(status, m->tmp_s.p, (size_t)batch * 4, 0);
+  if (!rc) rc = rt_sync(0);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,40 @@
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def H(s):
+    """hex string from the fixtures -> int (a leading '-' marks negative values)."""
+    return -int(s[1:], 16) if s.startswith("-") else int(s, 16)
+
+
+def load_golden(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    import paillier_b200
+    return paillier_b200
+
+
+@pytest.fixture(scope="session")
+def cuda_engine(pkg):
+    """The product engine (CUDA build).  GPU tests must run on it and nothing else."""
+    eng = pkg.get_engine()
+    eng.require_device()
+    assert eng.path.endswith("python-paillier_b200/libpaillier_b200.so")
+    return eng

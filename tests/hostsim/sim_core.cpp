@@ -1,0 +1,41 @@
+// TEST-ONLY host simulation of the device templates in pai_core.cuh (compiled with -DPAI_HOSTSIM).
+// Never part of the product library.
+#include <vector>
+#include <cstring>
+#include "../../python-paillier_b200/csrc/pai_core.cuh"
+using namespace pai;
+
+template <int NT>
+static void run_mont(int sqr, const uint32_t* a, const uint32_t* b, const uint32_t* N, const uint32_t* ninv, uint32_t* out, int nthreads, int tid) {
+  // simulate the interleaved layout with `nthreads` lanes, computing only lane `tid`
+  const int Q = 2 * NT;
+  std::vector<u4> A(Q * nthreads), B(Q * nthreads), O(Q * nthreads), Nc(Q), NI(2);
+  memcpy(NI.data(), ninv, 32);
+  for (int q = 0; q < Q; q++) {
+    memcpy(&A[q * nthreads + tid], a + 4 * q, 16);
+    memcpy(&B[q * nthreads + tid], b + 4 * q, 16);
+    memcpy(&Nc[q], N + 4 * q, 16);
+  }
+  Opnd oa{A.data() + tid, nthreads}, ob{B.data() + tid, nthreads}, oo{O.data() + tid, nthreads}, on{Nc.data(), 1};
+  Opnd oni{NI.data(), 1};
+  if (sqr) mont_sqr<NT>(oo, oa, on, oni); else mont_mul<NT>(oo, oa, ob, on, oni);
+  for (int q = 0; q < Q; q++) memcpy(out + 4 * q, &O[q * nthreads + tid], 16);
+}
+
+extern "C" int sim_mont(int NT, int sqr, const uint32_t* a, const uint32_t* b, const uint32_t* N, const uint32_t* ninv, uint32_t* out) {
+  switch (NT) {
+    case 1: run_mont<1>(sqr, a, b, N, ninv, out, 3, 1); break;
+    case 2: run_mont<2>(sqr, a, b, N, ninv, out, 3, 2); break;
+    case 4: run_mont<4>(sqr, a, b, N, ninv, out, 5, 0); break;
+    case 8: run_mont<8>(sqr, a, b, N, ninv, out, 2, 1); break;
+    case 16: run_mont<16>(sqr, a, b, N, ninv, out, 4, 3); break;
+    case 24: run_mont<24>(sqr, a, b, N, ninv, out, 1, 0); break;
+    default: return -1;
+  }
+  return 0;
+}
+extern "C" void sim_tile(const uint32_t* a, const uint32_t* b, uint32_t* out16, uint32_t* lo8) {
+  Acc A; acc_clear(A); tile_mac(A, a, b);
+  uint32_t v[8]; acc_resolve_low(A, v); memcpy(out16, v, 32); acc_shift8(A); acc_resolve_low(A, v); memcpy(out16 + 8, v, 32);
+  mul_lo8(lo8, a, b);
+}
