@@ -3,7 +3,7 @@ import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import paillier_b200 as pb
-from tests.conftest import H, load_golden
+from oracle.golden import H, load_golden
 
 def run(kb, batch):
     fx = load_golden("vectors_%d.json" % kb)

@@ -8,21 +8,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-GOLDEN = os.path.join(ROOT, "tests", "golden")
+from oracle.golden import GOLDEN, H, load_golden  # noqa: E402,F401
 
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-
-
-def H(s):
-    """hex string from the fixtures -> int (a leading '-' marks negative values)."""
-    return -int(s[1:], 16) if s.startswith("-") else int(s, 16)
-
-
-def load_golden(name):
-    with open(os.path.join(GOLDEN, name)) as f:
-        return json.load(f)
 
 
 @pytest.fixture(scope="session")
