@@ -59,6 +59,7 @@ __global__ void k_indep(uint32_t* out, const uint32_t* in, long long* cyc) {
         if (OP == 3) asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d[i]) : "d"(da), "d"(db));
         if (OP == 4) asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+r"(lo[i]) : "r"(a & 31));
         if (OP == 5) asm volatile("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(lo[i]), "+r"(hi[i]) : "r"(a), "r"(b));
+        if (OP == 6) asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;" : "+r"(lo[i]), "+r"(hi[i]) : "r"(lo[(i + 1) % NACC]), "r"(b));
       }
     }
   }
@@ -121,8 +122,8 @@ int main() {
            first ? "" : ",\n", name, warps, r.per_clk_sm, r.mhz, r.ms);
     first = 0;
   };
-  int wlist[] = {4, 8, 16, 32};
-  for (int wi = 0; wi < 4; wi++) {
+  int wlist[] = {4, 8, 16};   // <= 16 warps/SM so that every CTA of the grid is co-resident
+  for (int wi = 0; wi < 3; wi++) {
     int warps = wlist[wi]; int block = 128; int cta_per_sm = warps / 4; int grid = nsm * cta_per_sm;
     emit("wide_chain4_x2(IMAD.WIDE.X)", warps, run([&](uint32_t* o, const uint32_t* i, long long* c) { k_wide_chain<2><<<grid, block>>>(o, i, c); }, grid, block, 2.0 * 4 * ITERS, nsm));
     emit("wide_chain4_x4(IMAD.WIDE.X)", warps, run([&](uint32_t* o, const uint32_t* i, long long* c) { k_wide_chain<4><<<grid, block>>>(o, i, c); }, grid, block, 4.0 * 4 * ITERS, nsm));
@@ -130,6 +131,8 @@ int main() {
     emit("imad_lo", warps, run([&](uint32_t* o, const uint32_t* i, long long* c) { k_indep<0, 8><<<grid, block>>>(o, i, c); }, grid, block, 8.0 * 4 * ITERS, nsm));
     emit("imad_hi", warps, run([&](uint32_t* o, const uint32_t* i, long long* c) { k_indep<1, 8><<<grid, block>>>(o, i, c); }, grid, block, 8.0 * 4 * ITERS, nsm));
     emit("imad_wide_nocarry", warps, run([&](uint32_t* o, const uint32_t* i, long long* c) { k_indep<2, 8><<<grid, block>>>(o, i, c); }, grid, block, 8.0 * 4 * ITERS, nsm));
+    emit("imad_wide_pair_x8", warps, run([&](uint32_t* o, const uint32_t* i, long long* c) { k_indep<6, 8><<<grid, block>>>(o, i, c); }, grid, block, 8.0 * 4 * ITERS, nsm));
+    emit("imad_wide_pair_x16", warps, run([&](uint32_t* o, const uint32_t* i, long long* c) { k_indep<6, 16><<<grid, block>>>(o, i, c); }, grid, block, 16.0 * 4 * ITERS, nsm));
     emit("dfma", warps, run([&](uint32_t* o, const uint32_t* i, long long* c) { k_indep<3, 8><<<grid, block>>>(o, i, c); }, grid, block, 8.0 * 4 * ITERS, nsm));
     emit("shfl", warps, run([&](uint32_t* o, const uint32_t* i, long long* c) { k_indep<4, 8><<<grid, block>>>(o, i, c); }, grid, block, 8.0 * 4 * ITERS, nsm));
     emit("iadd_cc_pair", warps, run([&](uint32_t* o, const uint32_t* i, long long* c) { k_indep<5, 8><<<grid, block>>>(o, i, c); }, grid, block, 8.0 * 4 * ITERS * 2, nsm));

@@ -6,7 +6,7 @@
 #include "../python-paillier_b200/csrc/pai_core.cuh"
 using namespace pai;
 
-template <int NT, int NTHR>
+template <int NT, int NTHR, int VAR>
 __global__ void __launch_bounds__(NTHR, 1) k_rate(uint32_t* out, const uint32_t* in, int nsqr, int nmul, long long* cyc) {
   extern __shared__ u4 smem[];
   const int Q = 2 * NT;
@@ -21,8 +21,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_rate(uint32_t* out, const uint32_t*
   __syncthreads();
   Opnd X{bx + tid, NTHR}, Y{by + tid, NTHR}, Z{bz + tid, NTHR}, N{cst, 1}, ninv{cst + Q, 1};
   long long t0 = clock64();
-  for (int i = 0; i < nsqr; i++) { mont_sqr<NT>(Z, X, N, ninv); Opnd t = X; X = Z; Z = t; }
-  for (int i = 0; i < nmul; i++) { mont_mul<NT>(Z, X, Y, N, ninv); Opnd t = X; X = Z; Z = t; }
+  for (int i = 0; i < nsqr; i++) { if (VAR == 0) mont_sqr<NT>(Z, X, N, ninv); else mont_sqr2<NT>(Z, X, N, ninv); Opnd t = X; X = Z; Z = t; }
+  for (int i = 0; i < nmul; i++) { if (VAR == 0) mont_mul<NT>(Z, X, Y, N, ninv); else mont_mul2<NT>(Z, X, Y, N, ninv); Opnd t = X; X = Z; Z = t; }
   long long t1 = clock64();
   uint32_t s = 0;
   for (int q = 0; q < Q; q++) { u4 v = X.p[q * X.s]; s ^= v.x ^ v.y ^ v.z ^ v.w; }
@@ -30,22 +30,22 @@ __global__ void __launch_bounds__(NTHR, 1) k_rate(uint32_t* out, const uint32_t*
   if (tid == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
-template <int NT, int NTHR>
+template <int NT, int NTHR, int VAR>
 void bench(int nsqr, int nmul, const char* name) {
   cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
   int nsm = p.multiProcessorCount;
   size_t smem = (size_t)(2 * NT) * 16 * (1 + 3 * NTHR) + 32;
-  cudaFuncSetAttribute(k_rate<NT, NTHR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rate<NT, NTHR>, NTHR, smem);
+  cudaFuncSetAttribute(k_rate<NT, NTHR, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rate<NT, NTHR, VAR>, NTHR, smem);
   int grid = nsm * occ;
   uint32_t *out, *in; long long* cyc;
   cudaMalloc(&out, (size_t)grid * NTHR * 4); cudaMalloc(&in, 1 << 20); cudaMalloc(&cyc, grid * 8);
   cudaMemset(in, 0x5b, 1 << 20);
-  k_rate<NT, NTHR><<<grid, NTHR, smem>>>(out, in, nsqr, nmul, cyc);
+  k_rate<NT, NTHR, VAR><<<grid, NTHR, smem>>>(out, in, nsqr, nmul, cyc);
   cudaError_t e = cudaDeviceSynchronize();
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0);
-  k_rate<NT, NTHR><<<grid, NTHR, smem>>>(out, in, nsqr, nmul, cyc);
+  k_rate<NT, NTHR, VAR><<<grid, NTHR, smem>>>(out, in, nsqr, nmul, cyc);
   cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   long long* h = (long long*)malloc(grid * 8); cudaMemcpy(h, cyc, grid * 8, cudaMemcpyDeviceToHost);
@@ -54,22 +54,24 @@ void bench(int nsqr, int nmul, const char* name) {
   double tiles_mul = 2.0 * NT * NT + NT /*m*/ , tiles_sqr = NT * (NT - 1) / 2.0 + NT + NT * NT + NT;
   double macs = 64.0 * (nsqr * tiles_sqr + nmul * tiles_mul);
   double canon = (double)(nsqr + nmul) * (2.0 * (8 * NT) * (8 * NT) + 8 * NT);
-  printf("{\"kernel\": \"%s\", \"NT\": %d, \"threads\": %d, \"ctas_per_sm\": %d, \"err\": \"%s\", \"ms\": %.3f, \"cycles\": %.0f, "
+  printf("{\"kernel\": \"%s\", \"var\": %d, \"NT\": %d, \"threads\": %d, \"ctas_per_sm\": %d, \"err\": \"%s\", \"ms\": %.3f, \"cycles\": %.0f, "
          "\"exec_mac_per_clk_sm\": %.2f, \"canon_mac_per_clk_sm\": %.2f, \"modmul_per_s\": %.3e, \"canon_mac_per_s\": %.3e}\n",
-         name, NT, NTHR, occ, cudaGetErrorString(e), ms, mx, macs * NTHR * occ / mx, canon * NTHR * occ / mx,
+         name, VAR, NT, NTHR, occ, cudaGetErrorString(e), ms, mx, macs * NTHR * occ / mx, canon * NTHR * occ / mx,
          (double)(nsqr + nmul) * grid * NTHR / (ms * 1e-3), canon * grid * NTHR / (ms * 1e-3));
   free(h); cudaFree(out); cudaFree(in); cudaFree(cyc);
 }
 
 int main() {
-  bench<16, 128>(40, 0, "sqr4096");
-  bench<16, 128>(0, 40, "mul4096");
-  bench<16, 64>(40, 0, "sqr4096_64thr");
-  bench<8, 128>(80, 0, "sqr2048");
-  bench<8, 128>(0, 80, "mul2048");
-  bench<8, 256>(80, 0, "sqr2048_256thr");
-  bench<4, 128>(160, 0, "sqr1024");
-  bench<24, 64>(20, 0, "sqr6144_64thr");
-  bench<24, 96>(20, 0, "sqr6144_96thr");
+  bench<16, 128, 0>(40, 0, "sqr4096");
+  bench<16, 128, 1>(40, 0, "sqr4096");
+  bench<16, 128, 0>(0, 40, "mul4096");
+  bench<16, 128, 1>(0, 40, "mul4096");
+  bench<8, 128, 0>(80, 0, "sqr2048");
+  bench<8, 128, 1>(80, 0, "sqr2048");
+  bench<8, 128, 0>(0, 80, "mul2048");
+  bench<8, 128, 1>(0, 80, "mul2048");
+  bench<24, 96, 0>(20, 0, "sqr6144_96thr");
+  bench<24, 96, 1>(20, 0, "sqr6144_96thr");
+  bench<4, 128, 1>(160, 0, "sqr1024");
   return 0;
 }

@@ -7,4 +7,10 @@ The directory name carries a hyphen (it mirrors the reference repo's name), so i
 from .engine import (Engine, EngineError, EngineUnavailable, ModContext, PrivateContext, PublicContext,  # noqa: F401
                      get_engine, ints_to_limbs, limbs_to_ints)
 
+from .encoding import EncodedNumber  # noqa: F401,E402
+from .paillier import (DEFAULT_KEYSIZE, EncryptedNumber, PaillierPrivateKey, PaillierPrivateKeyring,  # noqa: F401,E402
+                       PaillierPublicKey, generate_paillier_keypair)
+from . import util  # noqa: F401,E402
+from .vector import EncryptedVector  # noqa: F401,E402
+
 __version__ = "0.1.0"

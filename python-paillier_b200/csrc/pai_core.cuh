@@ -445,4 +445,134 @@ PAI_FN void mont_sqr(Opnd out, Opnd a, Opnd N, Opnd NI) {
   big_cond_sub<NT>(out, N, ovf);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Variants with independent accumulators.  With one resident warp per scheduler (4096-bit moduli:
+// 3 x 512 B of shared memory per thread) a single accumulator serialises the two tile MACs of an
+// iteration; giving the product terms and the reduction terms their own accumulators (and, for the
+// square, the doubled off-diagonal terms a third one) lets ptxas interleave two independent
+// wavefronts of IMAD.WIDE chains.  The accumulators are never merged: each is shifted on its own and
+// only their low tiles are added when a column is finished.
+
+// v = low(A) + low(B) mod 2^256 without recording carries
+PAI_DEV void acc2_peek_low(const Acc& A, const Acc& B, uint32_t v[8]) {
+  uint32_t x[8], y[8];
+  acc_peek_low(A, x);
+  acc_peek_low(B, y);
+  add8(v, x, y);
+}
+// v = low(A) + low(B) mod 2^256, all carries recorded (in A.C[8] / B.C[8])
+PAI_DEV void acc2_resolve_low(Acc& A, Acc& B, uint32_t v[8]) {
+  uint32_t x[8], y[8];
+  acc_resolve_low(A, x);
+  acc_resolve_low(B, y);
+  A.C[8] += add8(v, x, y);
+}
+
+template <int NT>
+PAI_FN void mont_mul2(Opnd out, Opnd a, Opnd b, Opnd N, Opnd NI) {
+  Acc A, B;
+  acc_clear(A);
+  acc_clear(B);
+  uint32_t n0[8], ninv[8];
+  ld_tile(N, 0, n0);
+  ld_tile(NI, 0, ninv);
+  for (int k = 0; k < 2 * NT; k++) {
+    int lo = k - NT + 1 > 0 ? k - NT + 1 : 0;
+    int hi = k < NT ? k - 1 : NT - 1;
+    for (int i = lo; i <= hi; i++) {
+      uint32_t x[8], y[8], u[8], w[8];
+      ld_tile(a, i, x); ld_tile(b, k - i, y);
+      ld_tile(out, i, u); ld_tile(N, k - i, w);
+      tile_mac(A, x, y);
+      tile_mac(B, u, w);
+    }
+    uint32_t v[8];
+    if (k < NT) {
+      uint32_t x[8], y[8], m[8];
+      ld_tile(a, k, x); ld_tile(b, 0, y);
+      tile_mac(A, x, y);
+      acc2_peek_low(A, B, v);
+      mul_lo8(m, v, ninv);
+      st_tile(out, k, m);
+      tile_mac(B, m, n0);
+      acc2_resolve_low(A, B, v);
+    } else {
+      acc2_resolve_low(A, B, v);
+      st_tile(out, k - NT, v);
+    }
+    acc_shift8(A);
+    acc_shift8(B);
+  }
+  uint32_t ovf = A.E[0] + A.O[0] + A.C[0] + B.E[0] + B.O[0] + B.C[0];
+  big_cond_sub<NT>(out, N, ovf);
+}
+
+template <int NT>
+PAI_FN void mont_sqr2(Opnd out, Opnd a, Opnd N, Opnd NI) {
+  Acc A, B, S;
+  acc_clear(A);
+  acc_clear(B);
+  acc_clear(S);
+  uint32_t n0[8], ninv[8];
+  ld_tile(N, 0, n0);
+  ld_tile(NI, 0, ninv);
+  uint32_t topbit = 0;
+  for (int k = 0; k < 2 * NT; k++) {
+    int lo = k - NT + 1 > 0 ? k - NT + 1 : 0;
+    int hi = k < NT ? k - 1 : NT - 1;
+    int hs = k == 0 ? -1 : (k - 1) / 2;
+    int i = lo;
+    for (; i <= hs; i++) {                       // off-diagonal product tile + reduction tile
+      uint32_t x[8], y[8], u[8], w[8];
+      ld_tile(a, i, x); ld_tile(a, k - i, y);
+      ld_tile(out, i, u); ld_tile(N, k - i, w);
+      tile_mac(S, x, y);
+      tile_mac(A, u, w);
+    }
+    for (; i + 1 <= hi; i += 2) {                // remaining reduction tiles, two at a time
+      uint32_t x[8], y[8], u[8], w[8];
+      ld_tile(out, i, x); ld_tile(N, k - i, y);
+      ld_tile(out, i + 1, u); ld_tile(N, k - i - 1, w);
+      tile_mac(A, x, y);
+      tile_mac(B, u, w);
+    }
+    if (i <= hi) {
+      uint32_t x[8], y[8];
+      ld_tile(out, i, x); ld_tile(N, k - i, y);
+      tile_mac(A, x, y);
+    }
+    if ((k & 1) == 0) {
+      uint32_t x[8];
+      ld_tile(a, k >> 1, x);
+      tile_mac(B, x, x);
+    }
+    {
+      uint32_t d[8], d2[8];
+      acc_resolve_low(S, d);
+      acc_shift8(S);
+      d2[0] = (d[0] << 1) | topbit;
+      PAI_UNROLL
+      for (int j = 1; j < 8; j++) d2[j] = (d[j] << 1) | (d[j - 1] >> 31);
+      topbit = d[7] >> 31;
+      acc_add_low(A, d2);
+    }
+    uint32_t v[8];
+    if (k < NT) {
+      uint32_t m[8];
+      acc2_peek_low(A, B, v);
+      mul_lo8(m, v, ninv);
+      st_tile(out, k, m);
+      tile_mac(B, m, n0);
+      acc2_resolve_low(A, B, v);
+    } else {
+      acc2_resolve_low(A, B, v);
+      st_tile(out, k - NT, v);
+    }
+    acc_shift8(A);
+    acc_shift8(B);
+  }
+  uint32_t ovf = A.E[0] + A.O[0] + A.C[0] + B.E[0] + B.O[0] + B.C[0] + topbit;
+  big_cond_sub<NT>(out, N, ovf);
+}
+
 }  // namespace pai

@@ -47,7 +47,7 @@ PAI_DEV void cta_encrypt(u4* smem, const CtaId& id, int nwin, const uint32_t* m,
   ModC mc;
   modc_bind(mc, smem, NT);
   PowEnv<NT> E;
-  cta_bufs<NT>(E.buf, 3, smem, enc_const_quads<NT>(), id);
+  cta_bufs<NT>(E.buf, 2, smem, enc_const_quads<NT>(), id);       // two operand buffers (mont_pow2)
   E.tbl = cta_table<NT, W>(tbl, id);
   E.mc = &mc;
   Opnd nbc{smem + mc_limbs(NT) / 4, 1};
@@ -57,7 +57,7 @@ PAI_DEV void cta_encrypt(u4* smem, const CtaId& id, int nwin, const uint32_t* m,
     long g = chunk * id.nthr + id.tid;
     bool store = g < batch;
     if (!store) g = batch - 1;
-    prog_encrypt<NT, W>(E, nbc, e, ln, nwin, m + g * ln, r + g * ln, out + g * lc, store);
+    prog_encrypt2<NT, W>(E, nbc, e, ln, nwin, m + g * ln, r + g * ln, out + g * lc, store);
   }
 }
 

@@ -90,7 +90,11 @@ struct LBody {
 };
 
 const int W_ENC = 5, W_DEC = 5, W_VAR = 4;
-const int NTHR_MAX = 128;
+#if defined(PAI_HOSTSIM)
+const int NTHR_MAX = 2;      // the CPU simulation runs lanes one after the other: keep CTAs tiny
+#else
+const int NTHR_MAX = 256;
+#endif
 
 int pick_nt(int tiles_needed) {
   static const int sup[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
@@ -174,7 +178,7 @@ int geometry(int device, int NT, int const_quads, int nbuf, long batch, Geom& g)
   for (;;) {
     smem = ((size_t)const_quads + (size_t)nbuf * 2 * NT * nthr) * 16;
     if (smem <= max_smem || nthr <= 32) break;
-    nthr -= 32;
+    nthr -= 32;   // (never reached in the simulation build)
   }
   if (smem > max_smem) { g_err = "operand size does not fit shared memory"; return PAI_E_ARG; }
   int occ = rt_occupancy<Body>(nthr, smem);
@@ -323,7 +327,7 @@ int do_encrypt(pai_pub* k, const uint32_t* m_, const uint32_t* r, uint32_t* c, l
   pai_mod* m = k->nsq;
   Geom g;
   int cq = mc_limbs(NT) / 4 + NT;
-  int rc = geometry<B>(m->device, NT, cq, 3, batch, g);
+  int rc = geometry<B>(m->device, NT, cq, 2, batch, g);
   if (rc) return rc;
   rc = m->tbl.ensure(table_bytes(g, NT, W_ENC));
   if (rc) return rc;

@@ -126,6 +126,67 @@ PAI_DEV int mont_pow(const PowEnv<NT>& E, int bi, const uint32_t* e, int nl, int
   return cur;
 }
 
+// Two-buffer variant: table entries are consumed straight from the global table as the `b` operand of
+// mont_mul (never staged in shared memory), so a thread needs 2 x 32*NT bytes of shared memory instead
+// of 3 x -- at 4096-bit moduli that is 224 instead of 128 resident threads per SM.
+//   base (Montgomery form) in buf[bi] (bi in {0,1}); returns the buffer index of the result.
+template <int NT>
+PAI_DEV Opnd tbl_entry(const PowEnv<NT>& E, int e) {
+  Opnd o;
+  o.p = E.tbl.p + (size_t)e * 2 * NT * E.tbl.s;
+  o.s = E.tbl.s;
+  return o;
+}
+
+template <int NT, int W, bool SKIPZERO>
+PAI_DEV int mont_pow2(const PowEnv<NT>& E, int bi, const uint32_t* e, int nl, int nwin) {
+  const ModC& mc = *E.mc;
+  int cur = bi, oth = bi ^ 1;
+  if (nwin <= 0) {
+    big_copy<NT>(E.buf[oth], mc.R1);
+    return oth;
+  }
+  tbl_store<NT>(E, 0, mc.R1);
+  tbl_store<NT>(E, 1, E.buf[bi]);
+  const Opnd t1 = tbl_entry<NT>(E, 1);
+  mont_sqr<NT>(E.buf[oth], E.buf[cur], mc.N, mc.ninv);
+  { int t = cur; cur = oth; oth = t; }
+  tbl_store<NT>(E, 2, E.buf[cur]);
+  for (int i = 3; i < (1 << W); i++) {
+    mont_mul<NT>(E.buf[oth], E.buf[cur], t1, mc.N, mc.ninv);
+    { int t = cur; cur = oth; oth = t; }
+    tbl_store<NT>(E, i, E.buf[cur]);
+  }
+  tbl_load<NT>(E, (int)exp_digit(e, nl, (nwin - 1) * W, W), E.buf[cur]);
+  for (int wi = nwin - 2; wi >= 0; wi--) {
+    for (int s = 0; s < W; s++) {
+      mont_sqr<NT>(E.buf[oth], E.buf[cur], mc.N, mc.ninv);
+      int t = cur; cur = oth; oth = t;
+    }
+    int d = (int)exp_digit(e, nl, wi * W, W);
+    if (SKIPZERO && d == 0) continue;
+    mont_mul<NT>(E.buf[oth], E.buf[cur], tbl_entry<NT>(E, d), mc.N, mc.ninv);
+    int t = cur; cur = oth; oth = t;
+  }
+  return cur;
+}
+
+// raw_encrypt with two shared-memory buffers (see prog_encrypt below for the semantics)
+template <int NT, int W>
+PAI_DEV void prog_encrypt2(const PowEnv<NT>& E, const Opnd& nbc, const uint32_t* e, int nl, int nwin,
+                           const uint32_t* m_row, const uint32_t* r_row, uint32_t* out_row, bool store) {
+  const ModC& mc = *E.mc;
+  load_row(E.buf[0], r_row, NT, 2 * NT);
+  mont_mul<NT>(E.buf[1], E.buf[0], mc.R2, mc.N, mc.ninv);                 // r*R mod n^2
+  int cur = mont_pow2<NT, W, true>(E, 1, e, nl, nwin);                    // (r^n)*R mod n^2
+  tbl_store<NT>(E, 0, E.buf[cur]);                                        // park it in table slot 0
+  int a = cur, b = cur ^ 1;
+  load_row(E.buf[a], m_row, NT, NT);
+  big_mul<NT / 2, NT / 2, NT>(E.buf[b], E.buf[a], nbc, 1u);               // n*m + 1
+  mont_mul<NT>(E.buf[a], E.buf[b], tbl_entry<NT>(E, 0), mc.N, mc.ninv);   // (n*m+1) * r^n mod n^2
+  if (store) store_row(out_row, E.buf[a], 2 * NT);
+}
+
 // ------------------------------------------------------------------------------------------------
 // raw_encrypt:  c = (1 + n*m) * r^n mod n^2          (phe/paillier.py:102-139)
 // Both reference branches for the nude ciphertext (:125-134) equal n*(m mod n)+1 mod n^2

@@ -56,7 +56,7 @@ static inline int rt_sm_count(int dev) { int n = 0; cudaDeviceGetAttribute(&n, c
 static inline size_t rt_max_smem(int dev) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); return (size_t)n; }
 
 template <class Body>
-__global__ void __launch_bounds__(128) k_body(Body b) {
+__global__ void __launch_bounds__(256) k_body(Body b) {
   extern __shared__ u4 smem[];
   CtaId id{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
   cta_load_consts(smem, id, b.consts, b.const_quads);

@@ -1,0 +1,232 @@
+"""EncryptedVector: a batch of Paillier ciphertexts resident in GPU memory.
+
+The reference has no vector type: callers loop over scalars (examples/federated_learning_with_encryption.py
+:122-133, phe/tests/math_test.py:44-58).  This is the batched form of exactly those loops -- one kernel
+launch per vector operation, ciphertexts stay in HBM as [B, c_limbs] uint32 limb matrices and are
+only converted to Python ints on request.  Semantics per element are those of EncryptedNumber
+(exponent alignment before add, phe/paillier.py:695-700; lazy obfuscation, :565-566).
+"""
+import os
+
+import numpy as np
+
+from .encoding import EncodedNumber
+from .engine import ints_to_limbs, limbs_to_ints
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _to_dev(arr, device):
+    torch = _torch()
+    return torch.from_numpy(np.ascontiguousarray(arr).view(np.int32)).to("cuda:%d" % device, non_blocking=False)
+
+
+def _to_host(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+def random_r_values(n, count):
+    """count values uniform in [1, n) from os.urandom (64 surplus bits: bias < 2^-64), the batched
+    counterpart of PaillierPublicKey.get_random_lt_n (phe/paillier.py:141-143)."""
+    nbytes = (n.bit_length() + 7) // 8 + 8
+    raw = os.urandom(nbytes * count)
+    span = n - 1
+    return [1 + int.from_bytes(raw[i * nbytes:(i + 1) * nbytes], "little") % span for i in range(count)]
+
+
+class EncryptedVector(object):
+    def __init__(self, public_key, limbs, exponents, obfuscated=False):
+        self.public_key = public_key
+        self.limbs = limbs                                  # torch.int32 [B, c_limbs] on the key's device
+        self.exponents = np.asarray(exponents, dtype=np.int64)
+        self._obfuscated = obfuscated
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def encrypt(cls, public_key, values, precision=None, r_values=None):
+        """Encode every value (EncodedNumber.encode) and encrypt the batch in one launch.  With
+        r_values None each element gets a fresh random r and is therefore already obfuscated."""
+        encs = [v if isinstance(v, EncodedNumber) else EncodedNumber.encode(public_key, v, precision) for v in values]
+        return cls.encrypt_encoded(public_key, [e.encoding for e in encs], [e.exponent for e in encs], r_values)
+
+    @classmethod
+    def encrypt_encoded(cls, public_key, encodings, exponents, r_values=None):
+        ctx = public_key.engine_context()
+        count = len(encodings)
+        obf = r_values is None
+        if r_values is None:
+            r_values = random_r_values(public_key.n, count)
+        torch = _torch()
+        d_m = _to_dev(ints_to_limbs([e % public_key.n for e in encodings], ctx.n_limbs), ctx.device)
+        d_r = _to_dev(ints_to_limbs(list(r_values), ctx.n_limbs), ctx.device)
+        d_c = torch.empty((count, ctx.c_limbs), dtype=torch.int32, device=d_m.device)
+        if count:
+            ctx.encrypt_dev(d_m, d_r, d_c, count)
+        return cls(public_key, d_c, exponents, obfuscated=obf)
+
+    @classmethod
+    def from_encrypted_numbers(cls, numbers):
+        pk = numbers[0].public_key
+        ctx = pk.engine_context()
+        limbs = _to_dev(ints_to_limbs([x.ciphertext(be_secure=False) % pk.nsquare for x in numbers], ctx.c_limbs), ctx.device)
+        return cls(pk, limbs, [x.exponent for x in numbers])
+
+    # ------------------------------------------------------------------ access
+    def __len__(self):
+        return int(self.limbs.shape[0])
+
+    def ciphertexts(self, be_secure=True):
+        if be_secure and not self._obfuscated:
+            self.obfuscate()
+        return limbs_to_ints(_to_host(self.limbs))
+
+    def to_encrypted_numbers(self, be_secure=False):
+        from .paillier import EncryptedNumber
+        out = []
+        for c, e in zip(self.ciphertexts(be_secure), self.exponents.tolist()):
+            x = EncryptedNumber(self.public_key, c, int(e))
+            if self._obfuscated:
+                x._mark_obfuscated()
+            out.append(x)
+        return out
+
+    def __getitem__(self, i):
+        return self.to_encrypted_numbers()[i] if isinstance(i, int) else EncryptedVector(
+            self.public_key, self.limbs[i].contiguous(), self.exponents[i], self._obfuscated)
+
+    def obfuscate(self):
+        """c_i <- c_i * r_i^n mod n^2 with fresh r_i (phe/paillier.py:603-624): K1 with m = 0, then K3."""
+        ctx = self.public_key.engine_context()
+        count = len(self)
+        if count:
+            torch = _torch()
+            d_r = _to_dev(ints_to_limbs(random_r_values(self.public_key.n, count), ctx.n_limbs), ctx.device)
+            d_zero = torch.zeros((count, ctx.n_limbs), dtype=torch.int32, device=self.limbs.device)
+            d_rn = torch.empty_like(self.limbs)
+            ctx.encrypt_dev(d_zero, d_r, d_rn, count)
+            out = torch.empty_like(self.limbs)
+            ctx.raw_add_dev(self.limbs, d_rn, out, count)
+            self.limbs = out
+        self._obfuscated = True
+
+    # ------------------------------------------------------------------ arithmetic
+    def _raw_mul_rows(self, limbs, scalars):
+        """limbs[i] ^ scalars[i] mod n^2 (device), scalars: list of ints in [0, n)."""
+        ctx = self.public_key.engine_context()
+        torch = _torch()
+        count = int(limbs.shape[0])
+        d_s = _to_dev(ints_to_limbs(scalars, ctx.n_limbs), ctx.device)
+        out = torch.empty_like(limbs)
+        status = torch.zeros((count,), dtype=torch.int32, device=limbs.device)
+        ctx.raw_mul_dev(limbs, d_s, out, status, count)
+        if bool(status.any().item()):
+            raise ZeroDivisionError('invert() no inverse exists')
+        return out
+
+    def decrease_exponent_to(self, new_exps):
+        """Per-element exponent alignment: elements whose exponent is above new_exps[i] are raised to
+        BASE^(delta) (phe/paillier.py:570-601); the others are untouched."""
+        new_exps = np.broadcast_to(np.asarray(new_exps, dtype=np.int64), self.exponents.shape)
+        if np.any(new_exps > self.exponents):
+            raise ValueError('New exponent should be more negative than old exponent')
+        idx = np.nonzero(new_exps < self.exponents)[0]
+        limbs = self.limbs
+        if len(idx):
+            torch = _torch()
+            tidx = torch.from_numpy(idx).to(limbs.device)
+            factors = [pow(EncodedNumber.BASE, int(d)) for d in (self.exponents[idx] - new_exps[idx])]
+            encs = [EncodedNumber.encode(self.public_key, f).encoding for f in factors]
+            sub = self._raw_mul_rows(limbs[tidx].contiguous(), encs)
+            limbs = limbs.clone()
+            limbs[tidx] = sub
+        return EncryptedVector(self.public_key, limbs, new_exps.copy(), obfuscated=self._obfuscated and not len(idx))
+
+    def __add__(self, other):
+        ctx = self.public_key.engine_context()
+        torch = _torch()
+        if isinstance(other, EncryptedVector):
+            if self.public_key != other.public_key:
+                raise ValueError("Attempted to add numbers encrypted against different public keys!")
+            if len(other) != len(self):
+                raise ValueError("length mismatch")
+            new_exps = np.minimum(self.exponents, other.exponents)
+            a, b = self.decrease_exponent_to(new_exps), other.decrease_exponent_to(new_exps)
+            out = torch.empty_like(a.limbs)
+            if len(self):
+                ctx.raw_add_dev(a.limbs, b.limbs, out, len(self))
+            return EncryptedVector(self.public_key, out, new_exps)
+        # plaintext operand(s): encode against each element's exponent (phe/paillier.py:626-676)
+        scalars = list(other) if hasattr(other, "__len__") else [other] * len(self)
+        if len(scalars) != len(self):
+            raise ValueError("length mismatch")
+        encs = [s if isinstance(s, EncodedNumber) else EncodedNumber.encode(self.public_key, s, max_exponent=int(e))
+                for s, e in zip(scalars, self.exponents)]
+        new_exps = np.minimum(self.exponents, np.array([e.exponent for e in encs], dtype=np.int64))
+        a = self.decrease_exponent_to(new_exps)
+        encs = [e.decrease_exponent_to(int(x)) if e.exponent > x else e for e, x in zip(encs, new_exps)]
+        n = self.public_key.n
+        nude = [(n * e.encoding + 1) % self.public_key.nsquare for e in encs]      # raw_encrypt(., r=1), phe/paillier.py:673
+        d_b = _to_dev(ints_to_limbs(nude, ctx.c_limbs), ctx.device)
+        out = torch.empty_like(a.limbs)
+        if len(self):
+            ctx.raw_add_dev(a.limbs, d_b, out, len(self))
+        return EncryptedVector(self.public_key, out, new_exps)
+
+    __radd__ = __add__
+
+    def __mul__(self, other):
+        if isinstance(other, EncryptedVector):
+            raise NotImplementedError('Good luck with that...')
+        scalars = list(other) if hasattr(other, "__len__") else [other] * len(self)
+        if len(scalars) != len(self):
+            raise ValueError("length mismatch")
+        encs = [s if isinstance(s, EncodedNumber) else EncodedNumber.encode(self.public_key, s) for s in scalars]
+        out = self._raw_mul_rows(self.limbs, [e.encoding for e in encs]) if len(self) else self.limbs
+        return EncryptedVector(self.public_key, out, self.exponents + np.array([e.exponent for e in encs], dtype=np.int64))
+
+    __rmul__ = __mul__
+
+    def __sub__(self, other):
+        return self + (other * -1)
+
+    def __rsub__(self, other):
+        return other + (self * -1)
+
+    def __truediv__(self, scalar):
+        return self * (1 / scalar)
+
+    def sum(self):
+        """Homomorphic sum of all elements (product tree mod n^2) -> EncryptedNumber."""
+        from .paillier import EncryptedNumber
+        if not len(self):
+            raise ValueError("empty vector")
+        ctx = self.public_key.engine_context()
+        torch = _torch()
+        v = self.decrease_exponent_to(int(self.exponents.min()))
+        limbs = v.limbs
+        while limbs.shape[0] > 1:
+            half = limbs.shape[0] // 2
+            out = torch.empty((half, limbs.shape[1]), dtype=torch.int32, device=limbs.device)
+            ctx.raw_add_dev(limbs[:half].contiguous(), limbs[half:2 * half].contiguous(), out, half)
+            limbs = torch.cat([out, limbs[2 * half:]], dim=0) if limbs.shape[0] % 2 else out
+        c = limbs_to_ints(_to_host(limbs))[0]
+        return EncryptedNumber(self.public_key, c, int(v.exponents[0]))
+
+    # ------------------------------------------------------------------ decryption
+    def decrypt_encoded(self, private_key):
+        if self.public_key != private_key.public_key:
+            raise ValueError('encrypted_number was encrypted against a different key!')
+        ctx = private_key.engine_context()
+        torch = _torch()
+        count = len(self)
+        d_m = torch.empty((count, ctx.n_limbs), dtype=torch.int32, device=self.limbs.device)
+        if count:
+            ctx.decrypt_dev(self.limbs, d_m, count)
+        plain = limbs_to_ints(_to_host(d_m))
+        return [EncodedNumber(self.public_key, m, int(e)) for m, e in zip(plain, self.exponents)]
+
+    def decrypt(self, private_key):
+        return [e.decode() for e in self.decrypt_encoded(private_key)]

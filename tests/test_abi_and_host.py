@@ -1,0 +1,68 @@
+"""CPU checks of the product library: it loads, exports every symbol of include/paillier_b200.h, and
+refuses loudly to compute without a CUDA device (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle.golden import H, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as ge
+    ge.build()
+
+
+def test_header_symbols_exported(pkg, built):
+    hdr = open(os.path.join(ROOT, "include", "paillier_b200.h")).read()
+    declared = set(re.findall(r"\b(pai_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    engine_mod = __import__("importlib").import_module("python-paillier_b200.engine")
+    assert declared == set(engine_mod.SYMBOLS), declared ^ set(engine_mod.SYMBOLS)
+    eng = pkg.Engine()                      # the CUDA build, loaded through ctypes; binds every symbol
+    assert eng.path.endswith("libpaillier_b200.so")
+    assert eng.lib.pai_version() >= 100
+    assert eng.launch_count() == 0
+
+
+def test_no_cpu_fallback(pkg, built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the loud-failure path is for GPU-less hosts")
+    eng = pkg.Engine()
+    assert eng.device_count() == 0
+    with pytest.raises(pkg.EngineUnavailable):
+        pkg.PublicContext(H(load_golden("vectors_256.json")["n"]), engine=eng)
+    with pytest.raises(pkg.EngineUnavailable):
+        pkg.PrivateContext(293, 433, engine=eng)
+    with pytest.raises(pkg.EngineUnavailable):
+        pkg.ModContext(2 ** 127 - 1, engine=eng)
+    pk = pkg.PaillierPublicKey(H(load_golden("vectors_256.json")["n"]))
+    with pytest.raises(pkg.EngineUnavailable):
+        pk.encrypt(3)
+
+
+def test_limb_packing_roundtrip(pkg):
+    vals = [0, 1, 2 ** 32 - 1, 2 ** 32, 2 ** 255 + 12345, 2 ** 512 - 1]
+    arr = pkg.ints_to_limbs(vals, 16)
+    assert arr.shape == (6, 16) and arr.dtype == np.uint32 and arr[1, 0] == 1 and arr[3, 1] == 1
+    assert pkg.limbs_to_ints(arr) == vals
+    with pytest.raises(ValueError):
+        pkg.ints_to_limbs([2 ** 512], 16)
+    with pytest.raises(ValueError):
+        pkg.ints_to_limbs([-1], 16)
+
+
+def test_shard_range(pkg):
+    par = __import__("importlib").import_module("python-paillier_b200.parallel")
+    for batch in (0, 1, 7, 8, 1000, 4194304):
+        for world in (1, 2, 3, 8):
+            spans = [par.shard_range(batch, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == batch
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
