@@ -69,27 +69,45 @@ PAI_DEV void zero_tile(const Opnd& o, int t) {
 // ------------------------------------------------------------------------------------------------
 // Carry-chain primitives.  Each is ONE asm block so the carry flag never crosses a statement.
 
-// X[0..7] (four 64-bit aligned pairs) += {a0,a1,a2,a3} * b at pair offsets 0,2,4,6; carry-out -> cw
-PAI_DEV void mac_chain4(uint32_t* X, uint32_t& cw, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+PAI_DEV uint32_t lo32(uint64_t x) { return (uint32_t)x; }
+PAI_DEV uint32_t hi32(uint64_t x) { return (uint32_t)(x >> 32); }
+PAI_DEV uint64_t pack64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+// X[0..3] (four 64-bit column pairs) += {a0,a1,a2,a3} * b, one product per pair, carries rippling
+// from pair to pair; the final carry-out is added to cw.
+// The accumulator limbs are held as 64-bit values so that ptxas keeps every (lo, hi) in an aligned
+// register pair: each mad.lo.cc/madc.hi.cc couple becomes ONE in-place IMAD.WIDE.U32(.X) with no register
+// shuffling (with separate 32-bit registers the r01 ncu capture showed ~35 MOVs per 64 MACs).
+PAI_DEV void mac_chain4(uint64_t* X, uint32_t& cw, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
 #if !defined(PAI_HOSTSIM)
-  asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
-      "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
-      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
-      "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
-      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
-      "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
-      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
-      "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
-      "addc.u32 %8, %8, 0;"
-      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(cw)
+  asm("{\n\t"
+      ".reg .u32 l0, h0, l1, h1, l2, h2, l3, h3;\n\t"
+      "mov.b64 {l0, h0}, %0;\n\t"
+      "mov.b64 {l1, h1}, %1;\n\t"
+      "mov.b64 {l2, h2}, %2;\n\t"
+      "mov.b64 {l3, h3}, %3;\n\t"
+      "mad.lo.cc.u32 l0, %5, %9, l0;\n\t"
+      "madc.hi.cc.u32 h0, %5, %9, h0;\n\t"
+      "madc.lo.cc.u32 l1, %6, %9, l1;\n\t"
+      "madc.hi.cc.u32 h1, %6, %9, h1;\n\t"
+      "madc.lo.cc.u32 l2, %7, %9, l2;\n\t"
+      "madc.hi.cc.u32 h2, %7, %9, h2;\n\t"
+      "madc.lo.cc.u32 l3, %8, %9, l3;\n\t"
+      "madc.hi.cc.u32 h3, %8, %9, h3;\n\t"
+      "addc.u32 %4, %4, 0;\n\t"
+      "mov.b64 %0, {l0, h0};\n\t"
+      "mov.b64 %1, {l1, h1};\n\t"
+      "mov.b64 %2, {l2, h2};\n\t"
+      "mov.b64 %3, {l3, h3};\n\t"
+      "}"
+      : "+l"(X[0]), "+l"(X[1]), "+l"(X[2]), "+l"(X[3]), "+r"(cw)
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
 #else
   const uint32_t av[4] = {a0, a1, a2, a3};
   uint32_t c = 0;
   for (int i = 0; i < 4; i++) {
-    unsigned __int128 v = ((unsigned __int128)(((uint64_t)X[2 * i + 1] << 32) | X[2 * i])) + (uint64_t)av[i] * b + c;
-    X[2 * i] = (uint32_t)v;
-    X[2 * i + 1] = (uint32_t)(v >> 32);
+    unsigned __int128 v = (unsigned __int128)X[i] + (uint64_t)av[i] * b + c;
+    X[i] = (uint64_t)v;
     c = (uint32_t)(v >> 64);
   }
   cw += c;
@@ -176,19 +194,21 @@ PAI_DEV uint32_t sub8b(uint32_t r[8], const uint32_t a[8], const uint32_t b[8], 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Column accumulator.  Value = sum_i (E[i] + O[i] + C[i]) * 2^(32 i).
-//   E : targets of chains that start on an even column (pairs (0,1),(2,3),...)
-//   O : targets of chains that start on an odd column  (pairs (1,2),(3,4),...)
-//   C : small counters that collect the carry-out of every chain (never a product target, so they
-//       cannot overflow); keeping them separate makes every tile MAC exact without rippling.
+// Column accumulator.  Value = sum_i E[i]*2^(64 i) + sum_i O[i]*2^(64 i + 32) + sum_i C[i]*2^(32 i).
+//   E[i] : 64-bit pair on columns (2i, 2i+1)   -- targets of chains that start on an even column
+//   O[i] : 64-bit pair on columns (2i+1, 2i+2) -- targets of chains that start on an odd column
+//   C[i] : small counters that collect the carry-out of every chain (never a product target, so they
+//          cannot overflow); keeping them separate makes every tile MAC exact without rippling.
 struct Acc {
-  uint32_t E[16], O[16], C[17];
+  uint64_t E[8], O[8];
+  uint32_t C[17];
 };
 
 PAI_DEV void acc_clear(Acc& A) {
   PAI_UNROLL
-  for (int i = 0; i < 16; i++) { A.E[i] = 0; A.O[i] = 0; A.C[i] = 0; }
-  A.C[16] = 0;
+  for (int i = 0; i < 8; i++) { A.E[i] = 0; A.O[i] = 0; }
+  PAI_UNROLL
+  for (int i = 0; i < 17; i++) A.C[i] = 0;
 }
 
 // A += a[0..7] * b[0..7]   (64 wide MACs + 16 carry captures)
@@ -196,19 +216,31 @@ PAI_DEV void tile_mac(Acc& A, const uint32_t a[8], const uint32_t b[8]) {
   PAI_UNROLL
   for (int j = 0; j < 8; j++) {
     if ((j & 1) == 0) {
-      mac_chain4(&A.E[j], A.C[j + 8], a[0], a[2], a[4], a[6], b[j]);
-      mac_chain4(&A.O[j + 1], A.C[j + 9], a[1], a[3], a[5], a[7], b[j]);
+      mac_chain4(&A.E[j / 2], A.C[j + 8], a[0], a[2], a[4], a[6], b[j]);          // columns j   .. j+7
+      mac_chain4(&A.O[j / 2], A.C[j + 9], a[1], a[3], a[5], a[7], b[j]);          // columns j+1 .. j+8
     } else {
-      mac_chain4(&A.O[j], A.C[j + 8], a[0], a[2], a[4], a[6], b[j]);
-      mac_chain4(&A.E[j + 1], A.C[j + 9], a[1], a[3], a[5], a[7], b[j]);
+      mac_chain4(&A.O[(j - 1) / 2], A.C[j + 8], a[0], a[2], a[4], a[6], b[j]);    // columns j   .. j+7
+      mac_chain4(&A.E[(j + 1) / 2], A.C[j + 9], a[1], a[3], a[5], a[7], b[j]);    // columns j+1 .. j+8
     }
   }
 }
 
+// the low 8 columns of E and of O as 32-bit vectors
+PAI_DEV void acc_low_vectors(const Acc& A, uint32_t e[8], uint32_t o[8]) {
+  PAI_UNROLL
+  for (int i = 0; i < 4; i++) { e[2 * i] = lo32(A.E[i]); e[2 * i + 1] = hi32(A.E[i]); }
+  o[0] = 0;
+  o[1] = lo32(A.O[0]); o[2] = hi32(A.O[0]);
+  o[3] = lo32(A.O[1]); o[4] = hi32(A.O[1]);
+  o[5] = lo32(A.O[2]); o[6] = hi32(A.O[2]);
+  o[7] = lo32(A.O[3]);
+}
+
 // v = low 8 limbs of the accumulator value; their carry is pushed into C[8]
 PAI_DEV void acc_resolve_low(Acc& A, uint32_t v[8]) {
-  uint32_t t[8];
-  uint32_t c1 = add8(t, A.E, A.O);
+  uint32_t e[8], o[8], t[8];
+  acc_low_vectors(A, e, o);
+  uint32_t c1 = add8(t, e, o);
   uint32_t c2 = add8(v, t, A.C);
   A.C[8] += c1 + c2;
 }
@@ -216,38 +248,136 @@ PAI_DEV void acc_resolve_low(Acc& A, uint32_t v[8]) {
 // v = low 8 limbs of the accumulator value WITHOUT recording their carry (the limbs stay in place;
 // a later acc_resolve_low over the same limbs accounts for the carry exactly once)
 PAI_DEV void acc_peek_low(const Acc& A, uint32_t v[8]) {
-  uint32_t t[8];
-  add8(t, A.E, A.O);
+  uint32_t e[8], o[8], t[8];
+  acc_low_vectors(A, e, o);
+  add8(t, e, o);
   add8(v, t, A.C);
 }
 
 // A.low8 += d[0..7]  (carry captured in C[8])
 PAI_DEV void acc_add_low(Acc& A, const uint32_t d[8]) {
-  uint32_t t[8];
-  uint32_t c = add8(t, A.E, d);
+  uint32_t e[8], t[8];
   PAI_UNROLL
-  for (int i = 0; i < 8; i++) A.E[i] = t[i];
+  for (int i = 0; i < 4; i++) { e[2 * i] = lo32(A.E[i]); e[2 * i + 1] = hi32(A.E[i]); }
+  uint32_t c = add8(t, e, d);
+  PAI_UNROLL
+  for (int i = 0; i < 4; i++) A.E[i] = pack64(t[2 * i], t[2 * i + 1]);
   A.C[8] += c;
 }
 
 // A >>= 256 bits (the low 8 limbs must already have been consumed)
 PAI_DEV void acc_shift8(Acc& A) {
+  uint32_t straddle = hi32(A.O[3]);            // column 8 of the pair (7, 8): becomes column 0
   PAI_UNROLL
-  for (int i = 0; i < 8; i++) {
-    A.E[i] = A.E[i + 8]; A.E[i + 8] = 0;
-    A.O[i] = A.O[i + 8]; A.O[i + 8] = 0;
-    A.C[i] = A.C[i + 8]; A.C[i + 8] = 0;
-  }
+  for (int i = 0; i < 4; i++) { A.E[i] = A.E[i + 4]; A.E[i + 4] = 0; }
+  A.O[0] = A.O[4]; A.O[1] = A.O[5]; A.O[2] = A.O[6];
+  A.O[3] = 0; A.O[4] = 0; A.O[5] = 0; A.O[6] = 0;
+  PAI_UNROLL
+  for (int i = 0; i < 8; i++) { A.C[i] = A.C[i + 8]; A.C[i + 8] = 0; }
   A.C[8] = A.C[16];
   A.C[16] = 0;
+  uint64_t s = A.E[0] + straddle;               // fold it into the pair (0, 1); carry -> column 2
+  A.C[2] += (s < A.E[0]) ? 1u : 0u;
+  A.E[0] = s;
 }
 
-// m = (v * w) mod 2^256
+// Short chains for the truncated product below: X[0..NP) += {a0..} * b on NP pairs; the carry out of the
+// last pair is added to cw.
+template <int NP>
+PAI_DEV void mac_chain_n(uint64_t* X, uint32_t& cw, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+#if !defined(PAI_HOSTSIM)
+  if (NP == 1) {
+    asm("{\n\t.reg .u32 l0, h0;\n\t"
+        "mov.b64 {l0, h0}, %0;\n\t"
+        "mad.lo.cc.u32 l0, %2, %3, l0;\n\t"
+        "madc.hi.cc.u32 h0, %2, %3, h0;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        "mov.b64 %0, {l0, h0};\n\t}"
+        : "+l"(X[0]), "+r"(cw) : "r"(a0), "r"(b));
+  } else if (NP == 2) {
+    asm("{\n\t.reg .u32 l0, h0, l1, h1;\n\t"
+        "mov.b64 {l0, h0}, %0;\n\t"
+        "mov.b64 {l1, h1}, %1;\n\t"
+        "mad.lo.cc.u32 l0, %3, %5, l0;\n\t"
+        "madc.hi.cc.u32 h0, %3, %5, h0;\n\t"
+        "madc.lo.cc.u32 l1, %4, %5, l1;\n\t"
+        "madc.hi.cc.u32 h1, %4, %5, h1;\n\t"
+        "addc.u32 %2, %2, 0;\n\t"
+        "mov.b64 %0, {l0, h0};\n\t"
+        "mov.b64 %1, {l1, h1};\n\t}"
+        : "+l"(X[0]), "+l"(X[1]), "+r"(cw) : "r"(a0), "r"(a1), "r"(b));
+  } else if (NP == 3) {
+    asm("{\n\t.reg .u32 l0, h0, l1, h1, l2, h2;\n\t"
+        "mov.b64 {l0, h0}, %0;\n\t"
+        "mov.b64 {l1, h1}, %1;\n\t"
+        "mov.b64 {l2, h2}, %2;\n\t"
+        "mad.lo.cc.u32 l0, %4, %7, l0;\n\t"
+        "madc.hi.cc.u32 h0, %4, %7, h0;\n\t"
+        "madc.lo.cc.u32 l1, %5, %7, l1;\n\t"
+        "madc.hi.cc.u32 h1, %5, %7, h1;\n\t"
+        "madc.lo.cc.u32 l2, %6, %7, l2;\n\t"
+        "madc.hi.cc.u32 h2, %6, %7, h2;\n\t"
+        "addc.u32 %3, %3, 0;\n\t"
+        "mov.b64 %0, {l0, h0};\n\t"
+        "mov.b64 %1, {l1, h1};\n\t"
+        "mov.b64 %2, {l2, h2};\n\t}"
+        : "+l"(X[0]), "+l"(X[1]), "+l"(X[2]), "+r"(cw) : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+  } else {
+    mac_chain4(X, cw, a0, a1, a2, a3, b);
+  }
+#else
+  const uint32_t av[4] = {a0, a1, a2, a3};
+  uint32_t c = 0;
+  for (int i = 0; i < NP; i++) {
+    unsigned __int128 v = (unsigned __int128)X[i] + (uint64_t)av[i] * b + c;
+    X[i] = (uint64_t)v;
+    c = (uint32_t)(v >> 64);
+  }
+  cw += c;
+#endif
+}
+
+// m = (v * w) mod 2^256: only the products with i + j <= 7 matter, and those on the anti-diagonal
+// i + j = 7 only through their low halves: 28 wide MACs + 8 plain IMADs instead of 64 wide MACs.
 PAI_DEV void mul_lo8(uint32_t m[8], const uint32_t v[8], const uint32_t w[8]) {
-  Acc T;
-  acc_clear(T);
-  tile_mac(T, v, w);
-  acc_resolve_low(T, m);
+  uint64_t E[4] = {0, 0, 0, 0};    // column pairs (0,1) (2,3) (4,5) (6,7)
+  uint64_t O[3] = {0, 0, 0};       // column pairs (1,2) (3,4) (5,6)
+  // row j (multiplier w[j]); product v[i]*w[j] lands on columns (i+j, i+j+1) and is kept iff i + j <= 6
+  // j = 0: even i 0,2,4,6 -> E[0..3];  odd i 1,3,5 -> O[0..2]
+  uint32_t d = 0, junk = 0;        // d: column 7 (carries out of the O chains + anti-diagonal); junk: column 8
+  mac_chain_n<4>(&E[0], junk, v[0], v[2], v[4], v[6], w[0]);
+  mac_chain_n<3>(&O[0], d, v[1], v[3], v[5], 0, w[0]);
+  // j = 1: even i 0,2,4 -> O[0..2];   odd i 1,3,5 -> E[1..3]
+  mac_chain_n<3>(&O[0], d, v[0], v[2], v[4], 0, w[1]);
+  mac_chain_n<3>(&E[1], junk, v[1], v[3], v[5], 0, w[1]);
+  // j = 2: even i 0,2,4 -> E[1..3];   odd i 1,3 -> O[1..2]
+  mac_chain_n<3>(&E[1], junk, v[0], v[2], v[4], 0, w[2]);
+  mac_chain_n<2>(&O[1], d, v[1], v[3], 0, 0, w[2]);
+  // j = 3: even i 0,2 -> O[1..2];     odd i 1,3 -> E[2..3]
+  mac_chain_n<2>(&O[1], d, v[0], v[2], 0, 0, w[3]);
+  mac_chain_n<2>(&E[2], junk, v[1], v[3], 0, 0, w[3]);
+  // j = 4: even i 0,2 -> E[2..3];     odd i 1 -> O[2]
+  mac_chain_n<2>(&E[2], junk, v[0], v[2], 0, 0, w[4]);
+  mac_chain_n<1>(&O[2], d, v[1], 0, 0, 0, w[4]);
+  // j = 5: even i 0 -> O[2];          odd i 1 -> E[3]
+  mac_chain_n<1>(&O[2], d, v[0], 0, 0, 0, w[5]);
+  mac_chain_n<1>(&E[3], junk, v[1], 0, 0, 0, w[5]);
+  // j = 6: even i 0 -> E[3]
+  mac_chain_n<1>(&E[3], junk, v[0], 0, 0, 0, w[6]);
+  // anti-diagonal, low halves only -> column 7
+  PAI_UNROLL
+  for (int i = 0; i < 8; i++) d += v[i] * w[7 - i];
+  uint32_t e[8], o[8], t[8];
+  PAI_UNROLL
+  for (int i = 0; i < 4; i++) { e[2 * i] = lo32(E[i]); e[2 * i + 1] = hi32(E[i]); }
+  o[0] = 0;
+  o[1] = lo32(O[0]); o[2] = hi32(O[0]);
+  o[3] = lo32(O[1]); o[4] = hi32(O[1]);
+  o[5] = lo32(O[2]); o[6] = hi32(O[2]);
+  o[7] = d;
+  add8(t, e, o);
+  PAI_UNROLL
+  for (int i = 0; i < 8; i++) m[i] = t[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -322,7 +452,7 @@ template <int NTA, int NTB, int NCOL>
 PAI_DEV void big_mul(const Opnd& out, const Opnd& a, const Opnd& b, uint32_t addend) {
   Acc acc;
   acc_clear(acc);
-  acc.E[0] = addend;
+  acc.E[0] = addend;   // 64-bit pair on columns (0, 1)
   for (int k = 0; k < NCOL; k++) {
     int lo = k - NTB + 1 > 0 ? k - NTB + 1 : 0;
     int hi = k < NTA - 1 ? k : NTA - 1;
@@ -378,7 +508,7 @@ PAI_FN void mont_mul(Opnd out, Opnd a, Opnd b, Opnd N, Opnd NI) {
     }
     acc_shift8(acc);
   }
-  uint32_t ovf = acc.E[0] + acc.O[0] + acc.C[0];
+  uint32_t ovf = lo32(acc.E[0]) + acc.C[0];   // what is left is 0 or 1, in column 0
   big_cond_sub<NT>(out, N, ovf);
 }
 
@@ -441,137 +571,7 @@ PAI_FN void mont_sqr(Opnd out, Opnd a, Opnd N, Opnd NI) {
     }
     acc_shift8(acc);
   }
-  uint32_t ovf = acc.E[0] + acc.O[0] + acc.C[0] + topbit;
-  big_cond_sub<NT>(out, N, ovf);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Variants with independent accumulators.  With one resident warp per scheduler (4096-bit moduli:
-// 3 x 512 B of shared memory per thread) a single accumulator serialises the two tile MACs of an
-// iteration; giving the product terms and the reduction terms their own accumulators (and, for the
-// square, the doubled off-diagonal terms a third one) lets ptxas interleave two independent
-// wavefronts of IMAD.WIDE chains.  The accumulators are never merged: each is shifted on its own and
-// only their low tiles are added when a column is finished.
-
-// v = low(A) + low(B) mod 2^256 without recording carries
-PAI_DEV void acc2_peek_low(const Acc& A, const Acc& B, uint32_t v[8]) {
-  uint32_t x[8], y[8];
-  acc_peek_low(A, x);
-  acc_peek_low(B, y);
-  add8(v, x, y);
-}
-// v = low(A) + low(B) mod 2^256, all carries recorded (in A.C[8] / B.C[8])
-PAI_DEV void acc2_resolve_low(Acc& A, Acc& B, uint32_t v[8]) {
-  uint32_t x[8], y[8];
-  acc_resolve_low(A, x);
-  acc_resolve_low(B, y);
-  A.C[8] += add8(v, x, y);
-}
-
-template <int NT>
-PAI_FN void mont_mul2(Opnd out, Opnd a, Opnd b, Opnd N, Opnd NI) {
-  Acc A, B;
-  acc_clear(A);
-  acc_clear(B);
-  uint32_t n0[8], ninv[8];
-  ld_tile(N, 0, n0);
-  ld_tile(NI, 0, ninv);
-  for (int k = 0; k < 2 * NT; k++) {
-    int lo = k - NT + 1 > 0 ? k - NT + 1 : 0;
-    int hi = k < NT ? k - 1 : NT - 1;
-    for (int i = lo; i <= hi; i++) {
-      uint32_t x[8], y[8], u[8], w[8];
-      ld_tile(a, i, x); ld_tile(b, k - i, y);
-      ld_tile(out, i, u); ld_tile(N, k - i, w);
-      tile_mac(A, x, y);
-      tile_mac(B, u, w);
-    }
-    uint32_t v[8];
-    if (k < NT) {
-      uint32_t x[8], y[8], m[8];
-      ld_tile(a, k, x); ld_tile(b, 0, y);
-      tile_mac(A, x, y);
-      acc2_peek_low(A, B, v);
-      mul_lo8(m, v, ninv);
-      st_tile(out, k, m);
-      tile_mac(B, m, n0);
-      acc2_resolve_low(A, B, v);
-    } else {
-      acc2_resolve_low(A, B, v);
-      st_tile(out, k - NT, v);
-    }
-    acc_shift8(A);
-    acc_shift8(B);
-  }
-  uint32_t ovf = A.E[0] + A.O[0] + A.C[0] + B.E[0] + B.O[0] + B.C[0];
-  big_cond_sub<NT>(out, N, ovf);
-}
-
-template <int NT>
-PAI_FN void mont_sqr2(Opnd out, Opnd a, Opnd N, Opnd NI) {
-  Acc A, B, S;
-  acc_clear(A);
-  acc_clear(B);
-  acc_clear(S);
-  uint32_t n0[8], ninv[8];
-  ld_tile(N, 0, n0);
-  ld_tile(NI, 0, ninv);
-  uint32_t topbit = 0;
-  for (int k = 0; k < 2 * NT; k++) {
-    int lo = k - NT + 1 > 0 ? k - NT + 1 : 0;
-    int hi = k < NT ? k - 1 : NT - 1;
-    int hs = k == 0 ? -1 : (k - 1) / 2;
-    int i = lo;
-    for (; i <= hs; i++) {                       // off-diagonal product tile + reduction tile
-      uint32_t x[8], y[8], u[8], w[8];
-      ld_tile(a, i, x); ld_tile(a, k - i, y);
-      ld_tile(out, i, u); ld_tile(N, k - i, w);
-      tile_mac(S, x, y);
-      tile_mac(A, u, w);
-    }
-    for (; i + 1 <= hi; i += 2) {                // remaining reduction tiles, two at a time
-      uint32_t x[8], y[8], u[8], w[8];
-      ld_tile(out, i, x); ld_tile(N, k - i, y);
-      ld_tile(out, i + 1, u); ld_tile(N, k - i - 1, w);
-      tile_mac(A, x, y);
-      tile_mac(B, u, w);
-    }
-    if (i <= hi) {
-      uint32_t x[8], y[8];
-      ld_tile(out, i, x); ld_tile(N, k - i, y);
-      tile_mac(A, x, y);
-    }
-    if ((k & 1) == 0) {
-      uint32_t x[8];
-      ld_tile(a, k >> 1, x);
-      tile_mac(B, x, x);
-    }
-    {
-      uint32_t d[8], d2[8];
-      acc_resolve_low(S, d);
-      acc_shift8(S);
-      d2[0] = (d[0] << 1) | topbit;
-      PAI_UNROLL
-      for (int j = 1; j < 8; j++) d2[j] = (d[j] << 1) | (d[j - 1] >> 31);
-      topbit = d[7] >> 31;
-      acc_add_low(A, d2);
-    }
-    uint32_t v[8];
-    if (k < NT) {
-      uint32_t m[8];
-      acc2_peek_low(A, B, v);
-      mul_lo8(m, v, ninv);
-      st_tile(out, k, m);
-      tile_mac(B, m, n0);
-      acc2_resolve_low(A, B, v);
-    } else {
-      acc2_resolve_low(A, B, v);
-      st_tile(out, k - NT, v);
-    }
-    acc_shift8(A);
-    acc_shift8(B);
-  }
-  uint32_t ovf = A.E[0] + A.O[0] + A.C[0] + B.E[0] + B.O[0] + B.C[0] + topbit;
+  uint32_t ovf = lo32(acc.E[0]) + acc.C[0] + topbit;
   big_cond_sub<NT>(out, N, ovf);
 }
 

@@ -15,6 +15,43 @@ struct CtaId {
   int tid, nthr, cta, ncta;
 };
 
+// Row scheduler of the persistent kernels.  Work is handed out in groups of 32 consecutive rows (one
+// group per warp per iteration) from a global counter, so a warp that has a scheduler to itself (e.g.
+// the 7th warp of a 224-thread CTA) simply takes more groups than warps that share one, and the last
+// wave of a launch balances itself.  The CPU simulation (no warps, no atomics) uses the equivalent
+// static round-robin.
+struct RowSched {
+  unsigned long long* counter;   // zeroed by the host before the launch
+  long ngroups;                  // ceil(batch / gw)
+  int gw;                        // rows per group: 32 (the simulation build runs CTAs narrower than a warp)
+  long sim_next, sim_stride;     // simulation only
+};
+PAI_DEV RowSched sched_init(const CtaId& id, unsigned long long* counter, long batch) {
+  RowSched s;
+  s.counter = counter;
+  s.gw = id.nthr < 32 ? id.nthr : 32;
+  s.ngroups = (batch + s.gw - 1) / s.gw;
+  const long warps_per_cta = (id.nthr + s.gw - 1) / s.gw;
+  s.sim_next = (long)id.cta * warps_per_cta + id.tid / s.gw;
+  s.sim_stride = (long)id.ncta * warps_per_cta;
+  return s;
+}
+// next row for this thread, or -1 when the batch is exhausted
+PAI_DEV long sched_next_row(RowSched& s, const CtaId& id) {
+  long grp;
+#if !defined(PAI_HOSTSIM)
+  unsigned long long w = 0;
+  if ((id.tid & 31) == 0) w = atomicAdd(s.counter, 1ull);
+  w = __shfl_sync(0xffffffffu, w, 0);
+  grp = (long)w;
+#else
+  grp = s.sim_next;
+  s.sim_next += s.sim_stride;
+#endif
+  if (grp >= s.ngroups) return -1;
+  return grp * s.gw + (id.tid % s.gw);
+}
+
 // phase 0: constants -> shared
 PAI_DEV void cta_load_consts(u4* smem, const CtaId& id, const uint32_t* src, int nquads) {
   const u4* s = (const u4*)src;
@@ -41,23 +78,31 @@ PAI_DEV Opnd cta_table(u4* tbl, const CtaId& id) {
 template <int NT>
 PAI_DEV int enc_const_quads() { return mc_limbs(NT) / 4 + NT; }
 
-template <int NT, int W>
-PAI_DEV void cta_encrypt(u4* smem, const CtaId& id, int nwin, const uint32_t* m, const uint32_t* r, uint32_t* out,
-                         long batch, u4* tbl) {
+// table slots per thread of the encrypt kernel: 2^(w-1) odd powers + base^2
+template <int NT>
+PAI_DEV Opnd cta_table_slots(u4* tbl, const CtaId& id, int slots) {
+  Opnd t;
+  t.p = tbl + (size_t)id.cta * ((size_t)slots * 2 * NT * id.nthr) + id.tid;
+  t.s = id.nthr;
+  return t;
+}
+
+template <int NT>
+PAI_DEV void cta_encrypt(u4* smem, const CtaId& id, const uint32_t* prog, int nops, int nodd, const uint32_t* m, const uint32_t* r,
+                         uint32_t* out, long batch, u4* tbl, unsigned long long* counter) {
   ModC mc;
   modc_bind(mc, smem, NT);
   PowEnv<NT> E;
   cta_bufs<NT>(E.buf, 2, smem, enc_const_quads<NT>(), id);       // two operand buffers (mont_pow2)
-  E.tbl = cta_table<NT, W>(tbl, id);
+  E.tbl = cta_table_slots<NT>(tbl, id, nodd + 1);
   E.mc = &mc;
   Opnd nbc{smem + mc_limbs(NT) / 4, 1};
-  const uint32_t* e = (const uint32_t*)(smem + mc_limbs(NT) / 4);
   const int ln = 4 * NT, lc = 8 * NT;
-  for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
-    long g = chunk * id.nthr + id.tid;
+  RowSched sched = sched_init(id, counter, batch);
+  for (long g = sched_next_row(sched, id); g >= 0; g = sched_next_row(sched, id)) {
     bool store = g < batch;
     if (!store) g = batch - 1;
-    prog_encrypt2<NT, W>(E, nbc, e, ln, nwin, m + g * ln, r + g * ln, out + g * lc, store);
+    prog_encrypt2<NT>(E, nbc, prog, nops, nodd, m + g * ln, r + g * ln, out + g * lc, store);
   }
 }
 
@@ -82,7 +127,7 @@ PAI_DEV void cta_mulmod(u4* smem, const CtaId& id, const uint32_t* a, const uint
 // (made warp-uniform on the device so that a warp never diverges in the ladder).
 template <int NT, int W>
 PAI_DEV void cta_powmod(u4* smem, const CtaId& id, const uint32_t* base, int base_tiles, const uint32_t* exp, int exp_limbs,
-                        long exp_stride, int nwin_fixed, uint32_t* out, long batch, u4* tbl) {
+                        long exp_stride, int nwin_fixed, uint32_t* out, long batch, u4* tbl, unsigned long long* counter) {
   ModC mc;
   modc_bind(mc, smem, NT);
   PowEnv<NT> E;
@@ -90,8 +135,8 @@ PAI_DEV void cta_powmod(u4* smem, const CtaId& id, const uint32_t* base, int bas
   E.tbl = cta_table<NT, W>(tbl, id);
   E.mc = &mc;
   const int l = 8 * NT;
-  for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
-    long g = chunk * id.nthr + id.tid;
+  RowSched sched = sched_init(id, counter, batch);
+  for (long g = sched_next_row(sched, id); g >= 0; g = sched_next_row(sched, id)) {
     bool store = g < batch;
     if (!store) g = batch - 1;
     const uint32_t* e = exp + g * exp_stride;
@@ -171,7 +216,8 @@ PAI_DEV void side_bind(SideC<NTP>& S, u4* base, int nwin) {
 }
 
 template <int NTP, int W>
-PAI_DEV void cta_decrypt(u4* smem, const CtaId& id, int nwin_p, int nwin_q, const uint32_t* c, uint32_t* out, long batch, u4* tbl) {
+PAI_DEV void cta_decrypt(u4* smem, const CtaId& id, int nwin_p, int nwin_q, const uint32_t* c, uint32_t* out, long batch, u4* tbl,
+                         unsigned long long* counter) {
   SideC<NTP> P, Qs;
   side_bind<NTP>(P, smem, nwin_p);
   side_bind<NTP>(Qs, smem + side_quads<NTP>(), nwin_q);
@@ -181,8 +227,8 @@ PAI_DEV void cta_decrypt(u4* smem, const CtaId& id, int nwin_p, int nwin_q, cons
   E.tbl = cta_table<2 * NTP, W>(tbl, id);
   E.mc = &P.sq;
   const int lc = 32 * NTP, ln = 16 * NTP;
-  for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
-    long g = chunk * id.nthr + id.tid;
+  RowSched sched = sched_init(id, counter, batch);
+  for (long g = sched_next_row(sched, id); g >= 0; g = sched_next_row(sched, id)) {
     bool store = g < batch;
     if (!store) g = batch - 1;
     prog_decrypt<NTP, W>(E, P, Qs, pinvqM, c + g * lc, out + g * ln, store);

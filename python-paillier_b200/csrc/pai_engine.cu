@@ -31,11 +31,12 @@ struct XinvBody {
   uint32_t* out; const uint32_t* x; int nl;
   PAI_MEM void run(u4*, const CtaId& id) const { if (id.tid == 0 && id.cta == 0) inv_mod_2k(out, x, nl); }
 };
-template <int NT, int W>
+template <int NT>
 struct EncBody {
   const uint32_t* consts; int const_quads;
-  int nwin; const uint32_t* m; const uint32_t* r; uint32_t* out; long batch; u4* tbl;
-  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_encrypt<NT, W>(smem, id, nwin, m, r, out, batch, tbl); }
+  const uint32_t* prog; int nops, nodd; const uint32_t* m; const uint32_t* r; uint32_t* out; long batch; u4* tbl;
+  unsigned long long* counter;
+  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_encrypt<NT>(smem, id, prog, nops, nodd, m, r, out, batch, tbl, counter); }
 };
 template <int NT>
 struct MulBody {
@@ -47,9 +48,9 @@ template <int NT, int W>
 struct PowBody {
   const uint32_t* consts; int const_quads;
   const uint32_t* base; int base_tiles; const uint32_t* exp; int exp_limbs; long exp_stride; int nwin_fixed;
-  uint32_t* out; long batch; u4* tbl;
+  uint32_t* out; long batch; u4* tbl; unsigned long long* counter;
   PAI_MEM void run(u4* smem, const CtaId& id) const {
-    cta_powmod<NT, W>(smem, id, base, base_tiles, exp, exp_limbs, exp_stride, nwin_fixed, out, batch, tbl);
+    cta_powmod<NT, W>(smem, id, base, base_tiles, exp, exp_limbs, exp_stride, nwin_fixed, out, batch, tbl, counter);
   }
 };
 template <int NT>
@@ -68,8 +69,8 @@ struct PrepBody {
 template <int NTP, int W>
 struct DecBody {
   const uint32_t* consts; int const_quads;
-  int nwin_p, nwin_q; const uint32_t* c; uint32_t* out; long batch; u4* tbl;
-  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_decrypt<NTP, W>(smem, id, nwin_p, nwin_q, c, out, batch, tbl); }
+  int nwin_p, nwin_q; const uint32_t* c; uint32_t* out; long batch; u4* tbl; unsigned long long* counter;
+  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_decrypt<NTP, W>(smem, id, nwin_p, nwin_q, c, out, batch, tbl, counter); }
 };
 // one CRT half with h = 1 (used once per key to derive hp / hq): out = L(g^(x-1) mod x^2) mod x
 template <int NTP, int W>
@@ -89,7 +90,7 @@ struct LBody {
   }
 };
 
-const int W_ENC = 5, W_DEC = 5, W_VAR = 4;
+const int W_ENC = 6, W_DEC = 5, W_VAR = 4;   // W_ENC: sliding window (32 odd powers); W_DEC/W_VAR: fixed windows
 #if defined(PAI_HOSTSIM)
 const int NTHR_MAX = 2;      // the CPU simulation runs lanes one after the other: keep CTAs tiny
 #else
@@ -155,6 +156,34 @@ limbs_t padded(const uint32_t* a, int n, int total) {
   return r;
 }
 
+// Sliding-window program of a public exponent (see mont_pow_prog): left-to-right, windows of at most w
+// bits that start and end on a 1 bit.  entry = (nsq << 16) | idx, idx = (window value - 1) / 2 or 0xffff.
+std::vector<uint32_t> sliding_program(const limbs_t& e, int w) {
+  std::vector<uint32_t> prog;
+  int nbits = bit_length(e);
+  auto bit = [&](int i) { return (e[i >> 5] >> (i & 31)) & 1u; };
+  int i = nbits - 1;
+  uint32_t pending = 0;                      // squarings owed before the next multiplication
+  bool first = true;
+  while (i >= 0) {
+    if (!bit(i)) { pending++; i--; continue; }
+    int l = std::min(w, i + 1);
+    while (!bit(i - l + 1)) l--;             // window [i-l+1, i] ends on a 1
+    uint32_t v = 0;
+    for (int k = 0; k < l; k++) v = (v << 1) | bit(i - k);
+    if (first) { prog.push_back((0u << 16) | ((v - 1) / 2)); first = false; }
+    else {
+      uint32_t nsq = pending + (uint32_t)l;
+      while (nsq > 0xfff0u) { prog.push_back((0xfff0u << 16) | 0xffffu); nsq -= 0xfff0u; }
+      prog.push_back((nsq << 16) | ((v - 1) / 2));
+    }
+    pending = 0;
+    i -= l;
+  }
+  while (pending > 0) { uint32_t c = std::min(pending, 0xfff0u); prog.push_back((c << 16) | 0xffffu); pending -= c; }
+  return prog;
+}
+
 struct DevBuf {
   void* p = nullptr; size_t bytes = 0;
   int ensure(size_t need) {
@@ -166,6 +195,23 @@ struct DevBuf {
     return 0;
   }
   void release() { rt_free(p); p = nullptr; bytes = 0; }
+};
+
+// work counters of the persistent kernels: a ring of zero-initialised 64-bit counters per context; each
+// launch takes the next one and re-zeroes it on the launch stream first (launches on one stream are
+// ordered, so a counter is never re-armed while a previous kernel still uses it unless > 64 launches
+// are in flight on different streams -- callers use one context per concurrently used stream).
+struct Counters {
+  DevBuf buf; int next = 0;
+  int take(rt_stream s, unsigned long long** out) {
+    int rc = buf.ensure(64 * 8);
+    if (rc) return rc;
+    unsigned long long* p = (unsigned long long*)buf.p + next;
+    next = (next + 1) % 64;
+    rc = rt_memset(p, 0, 8, s);
+    *out = p;
+    return rc;
+  }
 };
 
 // launch geometry for a body with `nbuf` operand buffers of NT tiles
@@ -198,6 +244,7 @@ struct pai_mod {
   uint32_t* d_blob = nullptr;       // mc_limbs(NT) (+ extra room requested by the owner)
   limbs_t h_N;                      // padded modulus
   DevBuf tbl, tmp_a, tmp_b, tmp_o, tmp_s, tmp_e;
+  Counters ctr;
 };
 struct pai_pub {
   pai_mod* nsq = nullptr;           // modulus n^2; its blob is followed by n (4*NT limbs) for encrypt
@@ -205,6 +252,8 @@ struct pai_pub {
   uint32_t* d_nth = nullptr;        // [ n | n - max_int ]  (ln limbs each) for raw_mul's branch test
   DevBuf w_base, w_exp, w_flag, h_m, h_r, h_c, h_s;
   limbs_t h_n;
+  uint32_t* d_prog = nullptr;       // sliding-window program of the exponent n (encrypt)
+  int nops = 0, nodd = 0;
 };
 struct pai_priv {
   int device = 0, NTP = 0;
@@ -213,6 +262,7 @@ struct pai_priv {
   int nwin_p = 0, nwin_q = 0;
   limbs_t h_p, h_q, h_pinv, h_hp, h_hq;   // 16*NTP limbs each (padded)
   DevBuf tbl, h_c, h_m;
+  Counters ctr;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -282,7 +332,7 @@ void mod_free(pai_mod* m) {
   if (!m) return;
   rt_set_device(m->device);
   rt_free(m->d_blob);
-  m->tbl.release(); m->tmp_a.release(); m->tmp_b.release(); m->tmp_o.release(); m->tmp_s.release(); m->tmp_e.release();
+  m->ctr.buf.release(); m->tbl.release(); m->tmp_a.release(); m->tmp_b.release(); m->tmp_o.release(); m->tmp_s.release(); m->tmp_e.release();
   delete m;
 }
 
@@ -306,7 +356,10 @@ int do_powmod(pai_mod* m, const uint32_t* base, int base_tiles, const uint32_t* 
   if (rc) return rc;
   rc = m->tbl.ensure(table_bytes(g, NT, W_VAR));
   if (rc) return rc;
-  B body{m->d_blob, cq, base, base_tiles, d_exp, exp_limbs, exp_stride, nwin_fixed, out, batch, (u4*)m->tbl.p};
+  unsigned long long* ctr = nullptr;
+  rc = m->ctr.take(s, &ctr);
+  if (rc) return rc;
+  B body{m->d_blob, cq, base, base_tiles, d_exp, exp_limbs, exp_stride, nwin_fixed, out, batch, (u4*)m->tbl.p, ctr};
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
 }
 
@@ -323,16 +376,18 @@ int do_invert(pai_mod* m, const uint32_t* a, int a_tiles, const int32_t* flags, 
 
 template <int NT>
 int do_encrypt(pai_pub* k, const uint32_t* m_, const uint32_t* r, uint32_t* c, long batch, rt_stream s) {
-  typedef EncBody<NT, W_ENC> B;
+  typedef EncBody<NT> B;
   pai_mod* m = k->nsq;
   Geom g;
   int cq = mc_limbs(NT) / 4 + NT;
   int rc = geometry<B>(m->device, NT, cq, 2, batch, g);
   if (rc) return rc;
-  rc = m->tbl.ensure(table_bytes(g, NT, W_ENC));
+  rc = m->tbl.ensure((size_t)g.grid * (size_t)(k->nodd + 1) * 2 * NT * g.nthr * 16);
   if (rc) return rc;
-  int nwin = (bit_length(k->h_n) + W_ENC - 1) / W_ENC;
-  B body{m->d_blob, cq, nwin, m_, r, c, batch, (u4*)m->tbl.p};
+  unsigned long long* ctr = nullptr;
+  rc = m->ctr.take(s, &ctr);
+  if (rc) return rc;
+  B body{m->d_blob, cq, k->d_prog, k->nops, k->nodd, m_, r, c, batch, (u4*)m->tbl.p, ctr};
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
 }
 
@@ -345,7 +400,10 @@ int do_decrypt(pai_priv* k, const uint32_t* c, uint32_t* out, long batch, rt_str
   if (rc) return rc;
   rc = k->tbl.ensure(table_bytes(g, 2 * NTP, W_DEC));
   if (rc) return rc;
-  B body{k->d_consts, cq, k->nwin_p, k->nwin_q, c, out, batch, (u4*)k->tbl.p};
+  unsigned long long* ctr = nullptr;
+  rc = k->ctr.take(s, &ctr);
+  if (rc) return rc;
+  B body{k->d_consts, cq, k->nwin_p, k->nwin_q, c, out, batch, (u4*)k->tbl.p, ctr};
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
 }
 
@@ -533,6 +591,12 @@ int pai_pub_create(const uint32_t* n, int limbs, int device, pai_pub** out) {
   if (!rc) rc = rt_malloc((void**)&k->d_nth, (size_t)2 * ln * 4);
   if (!rc) rc = rt_h2d(k->d_nth, nn.data(), (size_t)ln * 4, 0);
   if (!rc) rc = rt_h2d(k->d_nth + ln, thr.data(), (size_t)ln * 4, 0);
+  // exponent program for r^n: sliding windows of W_ENC bits over the public exponent n
+  std::vector<uint32_t> prog = sliding_program(nn, W_ENC);
+  k->nops = (int)prog.size();
+  k->nodd = 1 << (W_ENC - 1);
+  if (!rc) rc = rt_malloc((void**)&k->d_prog, prog.size() * 4 + 16);
+  if (!rc) rc = rt_h2d(k->d_prog, prog.data(), prog.size() * 4, 0);
   if (!rc) rc = rt_sync(0);
   if (rc) { pai_pub_destroy(k); return rc; }
   *out = k;
@@ -542,6 +606,7 @@ int pai_pub_destroy(pai_pub* k) {
   if (!k) return 0;
   if (k->nsq) rt_set_device(k->nsq->device);
   rt_free(k->d_nth);
+  rt_free(k->d_prog);
   k->w_base.release(); k->w_exp.release(); k->w_flag.release(); k->h_m.release(); k->h_r.release(); k->h_c.release(); k->h_s.release();
   mod_free(k->nsq);
   delete k;
@@ -623,7 +688,7 @@ int pai_priv_destroy(pai_priv* k) {
     rt_sync(0);
   }
   rt_free(k->d_consts);
-  k->tbl.release(); k->h_c.release(); k->h_m.release();
+  k->ctr.buf.release(); k->tbl.release(); k->h_c.release(); k->h_m.release();
   mod_free(k->p2); mod_free(k->q2); mod_free(k->p1); mod_free(k->q1);
   std::fill(k->h_p.begin(), k->h_p.end(), 0); std::fill(k->h_q.begin(), k->h_q.end(), 0);
   delete k;

@@ -171,14 +171,54 @@ PAI_DEV int mont_pow2(const PowEnv<NT>& E, int bi, const uint32_t* e, int nl, in
   return cur;
 }
 
+// Sliding-window exponentiation driven by a host-built "exponent program" (public exponent shared by
+// the whole batch: encrypt's n).  prog[i] = (nsq << 16) | idx : square nsq times, then multiply by the
+// odd power T[idx] = base^(2 idx + 1)  (idx = 0xffff: no multiplication).  prog[0] only selects the
+// initial value T[idx].  Table slots: T[0 .. 2^(w-1)) odd powers, slot 2^(w-1) = base^2 (build helper).
+// Two shared-memory buffers, table entries consumed from global memory like mont_pow2.
+template <int NT>
+PAI_DEV int mont_pow_prog(const PowEnv<NT>& E, int bi, const uint32_t* prog, int nops, int nodd) {
+  const ModC& mc = *E.mc;
+  int cur = bi, oth = bi ^ 1;
+  if (nops <= 0) {                                   // exponent 0
+    big_copy<NT>(E.buf[oth], mc.R1);
+    return oth;
+  }
+  tbl_store<NT>(E, 0, E.buf[cur]);                                        // T[0] = base
+  if (nodd > 1) {
+    mont_sqr<NT>(E.buf[oth], E.buf[cur], mc.N, mc.ninv);                  // base^2
+    tbl_store<NT>(E, nodd, E.buf[oth]);
+    const Opnd b2 = tbl_entry<NT>(E, nodd);
+    for (int k = 1; k < nodd; k++) {                                      // T[k] = T[k-1] * base^2
+      mont_mul<NT>(E.buf[oth], E.buf[cur], b2, mc.N, mc.ninv);
+      { int t = cur; cur = oth; oth = t; }
+      tbl_store<NT>(E, k, E.buf[cur]);
+    }
+  }
+  tbl_load<NT>(E, (int)(prog[0] & 0xffffu), E.buf[cur]);
+  for (int i = 1; i < nops; i++) {
+    const uint32_t op = prog[i];
+    const int nsq = (int)(op >> 16), idx = (int)(op & 0xffffu);
+    for (int s = 0; s < nsq; s++) {
+      mont_sqr<NT>(E.buf[oth], E.buf[cur], mc.N, mc.ninv);
+      int t = cur; cur = oth; oth = t;
+    }
+    if (idx != 0xffff) {
+      mont_mul<NT>(E.buf[oth], E.buf[cur], tbl_entry<NT>(E, idx), mc.N, mc.ninv);
+      int t = cur; cur = oth; oth = t;
+    }
+  }
+  return cur;
+}
+
 // raw_encrypt with two shared-memory buffers (see prog_encrypt below for the semantics)
-template <int NT, int W>
-PAI_DEV void prog_encrypt2(const PowEnv<NT>& E, const Opnd& nbc, const uint32_t* e, int nl, int nwin,
+template <int NT>
+PAI_DEV void prog_encrypt2(const PowEnv<NT>& E, const Opnd& nbc, const uint32_t* prog, int nops, int nodd,
                            const uint32_t* m_row, const uint32_t* r_row, uint32_t* out_row, bool store) {
   const ModC& mc = *E.mc;
   load_row(E.buf[0], r_row, NT, 2 * NT);
   mont_mul<NT>(E.buf[1], E.buf[0], mc.R2, mc.N, mc.ninv);                 // r*R mod n^2
-  int cur = mont_pow2<NT, W, true>(E, 1, e, nl, nwin);                    // (r^n)*R mod n^2
+  int cur = mont_pow_prog<NT>(E, 1, prog, nops, nodd);                    // (r^n)*R mod n^2
   tbl_store<NT>(E, 0, E.buf[cur]);                                        // park it in table slot 0
   int a = cur, b = cur ^ 1;
   load_row(E.buf[a], m_row, NT, NT);

@@ -18,8 +18,7 @@ static void run_mont(int sqr, const uint32_t* a, const uint32_t* b, const uint32
   }
   Opnd oa{A.data() + tid, nthreads}, ob{B.data() + tid, nthreads}, oo{O.data() + tid, nthreads}, on{Nc.data(), 1};
   Opnd oni{NI.data(), 1};
-  if (sqr == 1) mont_sqr<NT>(oo, oa, on, oni); else if (sqr == 0) mont_mul<NT>(oo, oa, ob, on, oni);
-  else if (sqr == 3) mont_sqr2<NT>(oo, oa, on, oni); else mont_mul2<NT>(oo, oa, ob, on, oni);
+  if (sqr == 1) mont_sqr<NT>(oo, oa, on, oni); else mont_mul<NT>(oo, oa, ob, on, oni);
   for (int q = 0; q < Q; q++) memcpy(out + 4 * q, &O[q * nthreads + tid], 16);
 }
 
