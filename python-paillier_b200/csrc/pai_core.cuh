@@ -486,11 +486,11 @@ PAI_FN void mont_mul(Opnd out, Opnd a, Opnd b, Opnd N, Opnd NI) {
     int hi = k < NT ? k - 1 : NT - 1;
     // terms that have both a product and a reduction partner: i in [lo, hi], j = k - i >= 1
     for (int i = lo; i <= hi; i++) {
-      uint32_t x[8], y[8];
+      uint32_t x[8], y[8], u[8], w[8];
       ld_tile(a, i, x); ld_tile(b, k - i, y);
+      ld_tile(out, i, u); ld_tile(N, k - i, w);
       tile_mac(acc, x, y);
-      ld_tile(out, i, x); ld_tile(N, k - i, y);
-      tile_mac(acc, x, y);
+      tile_mac(acc, u, w);
     }
     uint32_t v[8];
     if (k < NT) {
@@ -530,13 +530,18 @@ PAI_FN void mont_sqr(Opnd out, Opnd a, Opnd N, Opnd NI) {
     // off-diagonal pairs i < j = k - i  <=>  i <= (k-1)/2
     int hs = (k - 1) / 2;
     if (k == 0) hs = -1;
-    for (int i = lo; i <= hs; i++) {
-      uint32_t x[8], y[8];
+    // i in [lo, hs]: an off-diagonal product tile (into S) and a reduction tile m_i * N_(k-i) (into acc) --
+    // two independent accumulators, so the two wavefronts of IMAD.WIDE chains interleave
+    int i = lo;
+    for (; i <= hs; i++) {
+      uint32_t x[8], y[8], u[8], w[8];
       ld_tile(a, i, x); ld_tile(a, k - i, y);
+      ld_tile(out, i, u); ld_tile(N, k - i, w);
       tile_mac(S, x, y);
+      tile_mac(acc, u, w);
     }
-    // reduction partners m_i * N_(k-i), i in [lo, hi]
-    for (int i = lo; i <= hi; i++) {
+    // remaining reduction partners, i in (hs, hi]
+    for (; i <= hi; i++) {
       uint32_t x[8], y[8];
       ld_tile(out, i, x); ld_tile(N, k - i, y);
       tile_mac(acc, x, y);

@@ -126,6 +126,8 @@ class Engine:
         except OSError as e:
             raise EngineUnavailable("cannot load %s: %s" % (path, e)) from e
         self.path = path
+        # the TEST-ONLY CPU simulation build treats "device" pointers as host pointers
+        self.simulated = "hostsim" in os.path.basename(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(self.lib, name)            # AttributeError if the ABI is incomplete
             fn.restype = res

@@ -19,9 +19,12 @@ def _torch():
     return torch
 
 
-def _to_dev(arr, device):
+def _to_dev(arr, ctx):
+    """numpy uint32 limb matrix -> torch.int32 tensor on the context's GPU (host tensor only for the test-only
+    simulation build, whose "device" pointers are host pointers)."""
     torch = _torch()
-    return torch.from_numpy(np.ascontiguousarray(arr).view(np.int32)).to("cuda:%d" % device, non_blocking=False)
+    t = torch.from_numpy(np.ascontiguousarray(arr).view(np.int32).copy())
+    return t if ctx.eng.simulated else t.to("cuda:%d" % ctx.device, non_blocking=False)
 
 
 def _to_host(t):
@@ -37,6 +40,116 @@ def random_r_values(n, count):
     return [1 + int.from_bytes(raw[i * nbytes:(i + 1) * nbytes], "little") % span for i in range(count)]
 
 
+# ------------------------------------------------------------------------------------------------------
+# Vectorised EncodedNumber.encode / decode (SURVEY.md section 8f, rank 1): numpy fast paths that give exactly
+# the values phe/encoding.py:110-233 computes element by element, with a per-element fallback for
+# everything outside the fast path (huge mantissas, precision=..., non-finite values, ints beyond 63 bits).
+def _limbs_from_signed(int_rep, n, ln):
+    """[B] int64 signed integers -> [B, ln] uint32 limbs of (int_rep mod n), assuming |int_rep| < 2^63 < n."""
+    mag = np.abs(int_rep).astype(np.uint64)
+    neg = int_rep < 0
+    out = np.zeros((int_rep.shape[0], ln), dtype=np.uint32)
+    out[:, 0] = (mag & np.uint64(0xffffffff)).astype(np.uint32)
+    if ln > 1:
+        out[:, 1] = (mag >> np.uint64(32)).astype(np.uint32)
+    if neg.any():
+        nl = ints_to_limbs([n], ln)[0]
+        n_low = np.uint64(int(nl[0]) | ((int(nl[1]) << 32) if ln > 1 else 0))
+        m = mag[neg]
+        low = n_low - m                                   # wraps modulo 2^64
+        borrow = m > n_low
+        rows = np.tile(nl, (m.shape[0], 1))
+        rows[:, 0] = (low & np.uint64(0xffffffff)).astype(np.uint32)
+        if ln > 1:
+            rows[:, 1] = (low >> np.uint64(32)).astype(np.uint32)
+        j = 2
+        while j < ln and borrow.any():
+            cur = rows[:, j]
+            rows[:, j] = np.where(borrow, cur - np.uint32(1), cur)
+            borrow = borrow & (cur == 0)
+            j += 1
+        out[neg] = rows
+    return out
+
+
+def encode_batch(public_key, values, precision=None, max_exponent=None):
+    """Encode a sequence like EncodedNumber.encode does element by element.
+    Returns (limbs [B, n_limbs] uint32 of the encodings, exponents [B] int64)."""
+    ctx = public_key.engine_context()
+    ln = ctx.n_limbs
+    arr = None
+    if precision is None and public_key.n.bit_length() > 80:
+        if isinstance(values, np.ndarray) and values.dtype in (np.float64, np.int64, np.int32):
+            arr = values
+        elif len(values) and all(type(v) is float for v in values):
+            arr = np.asarray(values, dtype=np.float64)
+        elif len(values) and all(type(v) is int and -2 ** 62 < v < 2 ** 62 for v in values):
+            arr = np.asarray(values, dtype=np.int64)
+    if arr is not None and arr.dtype == np.float64 and np.isfinite(arr).all():
+        m, e = np.frexp(arr)
+        mant = np.ldexp(m, 53).astype(np.int64)                       # exact 53-bit signed mantissa
+        lsb = e.astype(np.int64) - 53                                 # weight of the last mantissa bit
+        exps = np.floor_divide(lsb, 4)                                # floor(lsb / log2(16)), phe/encoding.py:167-174
+        if max_exponent is not None:
+            exps = np.minimum(exps, np.asarray(max_exponent, dtype=np.int64))
+        shift = lsb - 4 * exps
+        if (shift <= 9).all():                                        # |int_rep| < 2^62
+            int_rep = np.left_shift(mant, shift)
+            return _limbs_from_signed(int_rep, public_key.n, ln), exps
+    elif arr is not None and arr.dtype != np.float64:
+        exps = np.zeros(arr.shape[0], dtype=np.int64)
+        if max_exponent is None or (np.asarray(max_exponent) >= 0).all():
+            return _limbs_from_signed(arr.astype(np.int64), public_key.n, ln), exps
+    if isinstance(max_exponent, (list, tuple, np.ndarray)):
+        mex = [int(x) for x in max_exponent]
+    else:
+        mex = [max_exponent] * len(values)
+    vals = values.tolist() if isinstance(values, np.ndarray) else values
+    encs = [v if isinstance(v, EncodedNumber) else EncodedNumber.encode(public_key, v, precision, mx)
+            for v, mx in zip(vals, mex)]
+    return (ints_to_limbs([x.encoding for x in encs], ln), np.array([x.exponent for x in encs], dtype=np.int64))
+
+
+def decode_batch(public_key, limbs, exponents):
+    """Decode plaintext limbs [B, n_limbs] with exponents [B] like EncodedNumber.decode; returns a list."""
+    n = public_key.n
+    ln = limbs.shape[1]
+    count = limbs.shape[0]
+    out = [None] * count
+    exps = np.asarray(exponents, dtype=np.int64)
+    small_pos = ~limbs[:, 2:].any(axis=1) if ln > 2 else np.ones(count, dtype=bool)
+    low = limbs[:, 0].astype(np.uint64) | (limbs[:, 1].astype(np.uint64) << np.uint64(32)) if ln > 1 else limbs[:, 0].astype(np.uint64)
+    # n - enc for the candidates that are not small positives
+    nl = ints_to_limbs([n], ln)[0]
+    rest = np.nonzero(~small_pos)[0]
+    neg_small = np.zeros(count, dtype=bool)
+    neg_mag = np.zeros(count, dtype=np.uint64)
+    if len(rest):
+        rows = limbs[rest].astype(np.int64)
+        diff = np.zeros_like(rows)
+        borrow = np.zeros(len(rest), dtype=np.int64)
+        for j in range(ln):
+            d = np.int64(int(nl[j])) - rows[:, j] - borrow
+            borrow = (d < 0).astype(np.int64)
+            diff[:, j] = d + (borrow << 32)
+        ok = (borrow == 0) & ~(diff[:, 2:].any(axis=1) if ln > 2 else np.zeros(len(rest), dtype=bool))
+        neg_small[rest] = ok
+        neg_mag[rest] = diff[:, 0].astype(np.uint64) | ((diff[:, 1].astype(np.uint64) << np.uint64(32)) if ln > 1 else np.uint64(0))
+    fast = (small_pos | neg_small) & (exps < 0) & (exps > -250) & (public_key.max_int > 2 ** 64)
+    if fast.any():
+        mag = np.where(small_pos, low, neg_mag)
+        val = np.ldexp(mag.astype(np.float64), (4 * exps).astype(np.int32)) if EncodedNumber.BASE == 16 else None
+        val = np.where(small_pos, val, -val)
+        for i in np.nonzero(fast)[0]:
+            out[i] = float(val[i])
+    slow = np.nonzero(~fast)[0]
+    if len(slow):
+        encs = limbs_to_ints(limbs[slow])
+        for i, enc in zip(slow, encs):
+            out[i] = EncodedNumber(public_key, enc, int(exps[i])).decode()
+    return out
+
+
 class EncryptedVector(object):
     def __init__(self, public_key, limbs, exponents, obfuscated=False):
         self.public_key = public_key
@@ -49,19 +162,27 @@ class EncryptedVector(object):
     def encrypt(cls, public_key, values, precision=None, r_values=None):
         """Encode every value (EncodedNumber.encode) and encrypt the batch in one launch.  With
         r_values None each element gets a fresh random r and is therefore already obfuscated."""
-        encs = [v if isinstance(v, EncodedNumber) else EncodedNumber.encode(public_key, v, precision) for v in values]
-        return cls.encrypt_encoded(public_key, [e.encoding for e in encs], [e.exponent for e in encs], r_values)
+        if len(values) and any(isinstance(v, EncodedNumber) for v in (values if not isinstance(values, np.ndarray) else [])):
+            encs = [v if isinstance(v, EncodedNumber) else EncodedNumber.encode(public_key, v, precision) for v in values]
+            return cls.encrypt_encoded(public_key, [e.encoding for e in encs], [e.exponent for e in encs], r_values)
+        limbs, exps = encode_batch(public_key, values, precision)
+        return cls._encrypt_limbs(public_key, limbs, exps, r_values)
 
     @classmethod
     def encrypt_encoded(cls, public_key, encodings, exponents, r_values=None):
         ctx = public_key.engine_context()
-        count = len(encodings)
+        return cls._encrypt_limbs(public_key, ints_to_limbs([e % public_key.n for e in encodings], ctx.n_limbs), exponents, r_values)
+
+    @classmethod
+    def _encrypt_limbs(cls, public_key, m_limbs, exponents, r_values=None):
+        ctx = public_key.engine_context()
+        count = int(m_limbs.shape[0])
         obf = r_values is None
         if r_values is None:
             r_values = random_r_values(public_key.n, count)
         torch = _torch()
-        d_m = _to_dev(ints_to_limbs([e % public_key.n for e in encodings], ctx.n_limbs), ctx.device)
-        d_r = _to_dev(ints_to_limbs(list(r_values), ctx.n_limbs), ctx.device)
+        d_m = _to_dev(m_limbs, ctx)
+        d_r = _to_dev(ints_to_limbs(list(r_values), ctx.n_limbs), ctx)
         d_c = torch.empty((count, ctx.c_limbs), dtype=torch.int32, device=d_m.device)
         if count:
             ctx.encrypt_dev(d_m, d_r, d_c, count)
@@ -71,7 +192,7 @@ class EncryptedVector(object):
     def from_encrypted_numbers(cls, numbers):
         pk = numbers[0].public_key
         ctx = pk.engine_context()
-        limbs = _to_dev(ints_to_limbs([x.ciphertext(be_secure=False) % pk.nsquare for x in numbers], ctx.c_limbs), ctx.device)
+        limbs = _to_dev(ints_to_limbs([x.ciphertext(be_secure=False) % pk.nsquare for x in numbers], ctx.c_limbs), ctx)
         return cls(pk, limbs, [x.exponent for x in numbers])
 
     # ------------------------------------------------------------------ access
@@ -103,7 +224,7 @@ class EncryptedVector(object):
         count = len(self)
         if count:
             torch = _torch()
-            d_r = _to_dev(ints_to_limbs(random_r_values(self.public_key.n, count), ctx.n_limbs), ctx.device)
+            d_r = _to_dev(ints_to_limbs(random_r_values(self.public_key.n, count), ctx.n_limbs), ctx)
             d_zero = torch.zeros((count, ctx.n_limbs), dtype=torch.int32, device=self.limbs.device)
             d_rn = torch.empty_like(self.limbs)
             ctx.encrypt_dev(d_zero, d_r, d_rn, count)
@@ -118,7 +239,7 @@ class EncryptedVector(object):
         ctx = self.public_key.engine_context()
         torch = _torch()
         count = int(limbs.shape[0])
-        d_s = _to_dev(ints_to_limbs(scalars, ctx.n_limbs), ctx.device)
+        d_s = _to_dev(ints_to_limbs(scalars, ctx.n_limbs), ctx)
         out = torch.empty_like(limbs)
         status = torch.zeros((count,), dtype=torch.int32, device=limbs.device)
         ctx.raw_mul_dev(limbs, d_s, out, status, count)
@@ -169,7 +290,7 @@ class EncryptedVector(object):
         encs = [e.decrease_exponent_to(int(x)) if e.exponent > x else e for e, x in zip(encs, new_exps)]
         n = self.public_key.n
         nude = [(n * e.encoding + 1) % self.public_key.nsquare for e in encs]      # raw_encrypt(., r=1), phe/paillier.py:673
-        d_b = _to_dev(ints_to_limbs(nude, ctx.c_limbs), ctx.device)
+        d_b = _to_dev(ints_to_limbs(nude, ctx.c_limbs), ctx)
         out = torch.empty_like(a.limbs)
         if len(self):
             ctx.raw_add_dev(a.limbs, d_b, out, len(self))
@@ -229,4 +350,14 @@ class EncryptedVector(object):
         return [EncodedNumber(self.public_key, m, int(e)) for m, e in zip(plain, self.exponents)]
 
     def decrypt(self, private_key):
-        return [e.decode() for e in self.decrypt_encoded(private_key)]
+        """Decrypt and decode (vectorised EncodedNumber.decode) -> list of Python floats / ints."""
+        if self.public_key != private_key.public_key:
+            raise ValueError('encrypted_number was encrypted against a different key!')
+        ctx = private_key.engine_context()
+        torch = _torch()
+        count = len(self)
+        if not count:
+            return []
+        d_m = torch.empty((count, ctx.n_limbs), dtype=torch.int32, device=self.limbs.device)
+        ctx.decrypt_dev(self.limbs, d_m, count)
+        return decode_batch(self.public_key, _to_host(d_m), self.exponents)

@@ -1,0 +1,87 @@
+"""EncryptedVector and the vectorised EncodedNumber encode/decode on the test-only
+host simulation: results must equal the per-element reference semantics exactly."""
+import importlib
+import random
+
+import numpy as np
+import pytest
+
+from oracle.golden import H, load_golden
+
+
+@pytest.fixture(scope="module")
+def env(pkg):
+    import __graft_entry__ as ge
+    engine_mod = importlib.import_module("python-paillier_b200.engine")
+    engine_mod._set_engine_for_tests(pkg.Engine(ge.build_hostsim()))
+    fx = load_golden("vectors_256.json")
+    pk = pkg.PaillierPublicKey(H(fx["n"]))
+    sk = pkg.PaillierPrivateKey(pk, H(fx["p"]), H(fx["q"]))
+    yield pk, sk, importlib.import_module("python-paillier_b200.vector")
+    engine_mod._set_engine_for_tests(None)
+
+
+def test_encode_decode_batch_exact(pkg, env):
+    pk, sk, vec = env
+    rng = random.Random(1)
+    vals = [rng.gauss(0, 0.1) for _ in range(300)] + [0.0, -0.0, 1.0, -1.0, 1e-300, -1e-300, 1e30, -2.5e-7, float(2 ** 53), 0.1, 5e-324]
+    limbs, exps = vec.encode_batch(pk, vals)
+    ref = [pkg.EncodedNumber.encode(pk, v) for v in vals]
+    assert pkg.limbs_to_ints(limbs) == [e.encoding for e in ref] and exps.tolist() == [e.exponent for e in ref]
+    limbs, exps = vec.encode_batch(pk, np.array(vals))
+    assert pkg.limbs_to_ints(limbs) == [e.encoding for e in ref]
+    ivals = [rng.randrange(-2 ** 40, 2 ** 40) for _ in range(100)] + [0, 1, -1, 2 ** 61, -2 ** 61]
+    limbs, exps = vec.encode_batch(pk, ivals)
+    assert pkg.limbs_to_ints(limbs) == [pkg.EncodedNumber.encode(pk, v).encoding for v in ivals] and not exps.any()
+    limbs, exps = vec.encode_batch(pk, vals[:50], max_exponent=[-15] * 50)
+    ref15 = [pkg.EncodedNumber.encode(pk, v, max_exponent=-15) for v in vals[:50]]
+    assert pkg.limbs_to_ints(limbs) == [e.encoding for e in ref15] and exps.tolist() == [e.exponent for e in ref15]
+    mixed = [1, 2.5, -3, 10 ** 30]                        # falls back to the per-element path
+    limbs, exps = vec.encode_batch(pk, mixed)
+    assert pkg.limbs_to_ints(limbs) == [pkg.EncodedNumber.encode(pk, v).encoding for v in mixed]
+    with pytest.raises(ValueError):
+        vec.encode_batch(pk, [pk.max_int + 1, 1])
+    encs = ref + [pkg.EncodedNumber.encode(pk, float(v)) for v in ivals]
+    ln = pk.engine_context().n_limbs
+    dec = vec.decode_batch(pk, pkg.ints_to_limbs([e.encoding for e in encs], ln), [e.exponent for e in encs])
+    refd = [e.decode() for e in encs]
+    assert all(a == b and type(a) is type(b) for a, b in zip(dec, refd))
+    prods = [pkg.EncodedNumber(pk, (a.encoding * b.encoding) % pk.n, a.exponent + b.exponent) for a, b in zip(encs[:200], encs[100:300])]
+    dec = vec.decode_batch(pk, pkg.ints_to_limbs([e.encoding for e in prods], ln), [e.exponent for e in prods])
+    assert dec == [e.decode() for e in prods]
+    with pytest.raises(OverflowError):
+        vec.decode_batch(pk, pkg.ints_to_limbs([pk.max_int + 10], ln), [0])
+
+
+def test_vector_ops_match_scalar_semantics(pkg, env):
+    pk, sk, vec = env
+    rng = random.Random(4)
+    a = [rng.gauss(0, 1) for _ in range(9)] + [3, -4, 0]
+    b = [rng.gauss(0, 1e-3) for _ in range(9)] + [1.5, 2, -7]
+    ra = [rng.randrange(1, pk.n) for _ in a]
+    rb = [rng.randrange(1, pk.n) for _ in b]
+    va, vb = pk.encrypt_batch(a, r_values=ra), pk.encrypt_batch(b, r_values=rb)
+    sa = [pk.encrypt(x, r_value=r) for x, r in zip(a, ra)]
+    sb = [pk.encrypt(x, r_value=r) for x, r in zip(b, rb)]
+    assert va.ciphertexts(False) == [x.ciphertext(False) for x in sa]
+    for vres, sres in (((va + vb), [x + y for x, y in zip(sa, sb)]),
+                       ((va + b), [x + y for x, y in zip(sa, b)]),
+                       ((va * b), [x * y for x, y in zip(sa, b)]),
+                       ((va - vb), [x - y for x, y in zip(sa, sb)]),
+                       ((va / 4), [x / 4 for x in sa])):
+        assert vres.ciphertexts(False) == [x.ciphertext(False) for x in sres]
+        assert vres.exponents.tolist() == [x.exponent for x in sres]
+        assert sk.decrypt_batch(vres) == [sk.decrypt(x) for x in sres]
+    assert sk.decrypt((va + vb).sum()) == pytest.approx(sum(a) + sum(b), abs=1e-12)
+    fresh = pk.encrypt_batch(a)
+    c0 = fresh.ciphertexts(False)
+    assert fresh.ciphertexts(True) == c0                    # already obfuscated by the random r
+    s = va + vb
+    c1 = s.ciphertexts(False)
+    assert s.ciphertexts(True) != c1 and sk.decrypt_batch(s) == [sk.decrypt(x + y) for x, y in zip(sa, sb)]
+    back = pkg.EncryptedVector.from_encrypted_numbers(sa)
+    assert back.ciphertexts(False) == va.ciphertexts(False) and len(back) == len(a)
+    with pytest.raises(NotImplementedError):
+        va * vb
+    with pytest.raises(ValueError):
+        va + pk.encrypt_batch([1.0])
