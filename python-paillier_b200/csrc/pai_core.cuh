@@ -427,10 +427,11 @@ PAI_DEV uint32_t big_add_masked(const Opnd& out, const Opnd& a, const Opnd& b, u
 
 // x = x - N if (force || x >= N)    -> canonical residue when x < 2N (or x + force*2^(256NT) < 2N)
 template <int NT>
-PAI_DEV void big_cond_sub(const Opnd& x, const Opnd& N, uint32_t force) {
+PAI_DEV uint32_t big_cond_sub(const Opnd& x, const Opnd& N, uint32_t force) {
   uint32_t bo = big_sub_borrow<NT>(x, N);
-  uint32_t need = (force | (bo ^ 1u)) & 1u;
+  uint32_t need = ((force != 0u) | (bo ^ 1u)) & 1u;
   big_sub_masked<NT>(x, x, N, 0u - need);
+  return need;                                   // 1 iff N was subtracted
 }
 
 template <int NT>

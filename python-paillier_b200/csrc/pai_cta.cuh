@@ -8,6 +8,7 @@
 // tests/hostsim calls phase 0 for every simulated thread, then phase 1 for every simulated thread.
 #pragma once
 #include "pai_kernels.cuh"
+#include "pai_digit.cuh"
 
 namespace pai {
 
@@ -103,6 +104,26 @@ PAI_DEV void cta_encrypt(u4* smem, const CtaId& id, const uint32_t* prog, int no
     bool store = g < batch;
     if (!store) g = batch - 1;
     prog_encrypt2<NT>(E, nbc, prog, nops, nodd, m + g * ln, r + g * ln, out + g * lc, store);
+  }
+}
+
+// ---- encrypt in digit form (pai_digit.cuh).  consts = compact encrypt constants (dc_enc_limbs(NTH)); two buffers of
+// 2*NTH tiles per thread; r and m are read straight from their global rows.
+template <int NTH>
+PAI_DEV void cta_encrypt_digit(u4* smem, const CtaId& id, const uint32_t* prog, int nops, int nodd, const uint32_t* m,
+                               const uint32_t* r, uint32_t* out, long batch, u4* tbl, unsigned long long* counter) {
+  DigitEnv dc;
+  digit_bind_enc<NTH>(dc, smem);
+  DPowEnv<NTH> E;
+  cta_bufs<2 * NTH>(E.buf, 2, smem, dc_enc_limbs(NTH) / 4, id);
+  E.tbl = cta_table_slots<2 * NTH>(tbl, id, nodd + 1);
+  E.dc = &dc;
+  const int ln = 8 * NTH, lc = 16 * NTH;
+  RowSched sched = sched_init(id, counter, batch);
+  for (long g = sched_next_row(sched, id); g >= 0; g = sched_next_row(sched, id)) {
+    bool store = g < batch;
+    if (!store) g = batch - 1;
+    prog_encrypt_digit<NTH>(E, prog, nops, nodd, m + g * ln, r + g * ln, out + g * lc, store);
   }
 }
 

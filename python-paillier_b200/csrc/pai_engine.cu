@@ -38,6 +38,19 @@ struct EncBody {
   unsigned long long* counter;
   PAI_MEM void run(u4* smem, const CtaId& id) const { cta_encrypt<NT>(smem, id, prog, nops, nodd, m, r, out, batch, tbl, counter); }
 };
+template <int NTH>
+struct DigitSetupBody {
+  const uint32_t* consts; int const_quads;
+  uint32_t* blob; uint32_t* scratch;
+  PAI_MEM void run(u4*, const CtaId& id) const { if (id.tid == 0 && id.cta == 0) digit_setup<NTH>(blob, scratch); }
+};
+template <int NTH>
+struct EncDigitBody {
+  const uint32_t* consts; int const_quads;
+  const uint32_t* prog; int nops, nodd; const uint32_t* m; const uint32_t* r; uint32_t* out; long batch; u4* tbl;
+  unsigned long long* counter;
+  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_encrypt_digit<NTH>(smem, id, prog, nops, nodd, m, r, out, batch, tbl, counter); }
+};
 template <int NT>
 struct MulBody {
   const uint32_t* consts; int const_quads;
@@ -254,6 +267,9 @@ struct pai_pub {
   limbs_t h_n;
   uint32_t* d_prog = nullptr;       // sliding-window program of the exponent n (encrypt)
   int nops = 0, nodd = 0;
+  pai_mod* nmod = nullptr;          // modulus n with the digit-form constants appended (pai_digit.cuh)
+  uint32_t* d_enc_consts = nullptr; // compact constant area of the encrypt kernel (dc_enc_limbs)
+  bool use_digit = true;            // PAI_ENCRYPT_PATH=full selects the full-width Montgomery path instead
 };
 struct pai_priv {
   int device = 0, NTP = 0;
@@ -288,6 +304,17 @@ struct pai_priv {
     case 4: { constexpr int NTP = 4; CALL; } break;                                                   \
     case 6: { constexpr int NTP = 6; CALL; } break;                                                   \
     case 8: { constexpr int NTP = 8; CALL; } break;                                                   \
+    default: g_err = "unsupported key size"; rc = PAI_E_ARG;                                          \
+  }
+
+#define DISPATCH_NTH(NTV, CALL)                                                                       \
+  switch (NTV) {                                                                                      \
+    case 2: { constexpr int NTH = 2; CALL; } break;                                                   \
+    case 4: { constexpr int NTH = 4; CALL; } break;                                                   \
+    case 6: { constexpr int NTH = 6; CALL; } break;                                                   \
+    case 8: { constexpr int NTH = 8; CALL; } break;                                                   \
+    case 12: { constexpr int NTH = 12; CALL; } break;                                                 \
+    case 16: { constexpr int NTH = 16; CALL; } break;                                                 \
     default: g_err = "unsupported key size"; rc = PAI_E_ARG;                                          \
   }
 
@@ -388,6 +415,35 @@ int do_encrypt(pai_pub* k, const uint32_t* m_, const uint32_t* r, uint32_t* c, l
   rc = m->ctr.take(s, &ctr);
   if (rc) return rc;
   B body{m->d_blob, cq, k->d_prog, k->nops, k->nodd, m_, r, c, batch, (u4*)m->tbl.p, ctr};
+  return rt_launch(body, g.grid, g.nthr, g.smem, s);
+}
+
+template <int NTH>
+int do_digit_setup(pai_mod* m, rt_stream s) {
+  void* scratch = nullptr;
+  int rc = rt_malloc(&scratch, (size_t)4 * 8 * NTH * 4);
+  if (rc) return rc;
+  DigitSetupBody<NTH> b{nullptr, 0, m->d_blob, (uint32_t*)scratch};
+  rc = rt_launch(b, 1, 32, 0, s);
+  if (!rc) rc = rt_sync(s);
+  rt_free(scratch);
+  return rc;
+}
+
+template <int NTH>
+int do_encrypt_digit(pai_pub* k, const uint32_t* m_, const uint32_t* r, uint32_t* c, long batch, rt_stream s) {
+  typedef EncDigitBody<NTH> B;
+  pai_mod* m = k->nmod;
+  Geom g;
+  int cq = dc_enc_limbs(NTH) / 4;
+  int rc = geometry<B>(m->device, 2 * NTH, cq, 2, batch, g);
+  if (rc) return rc;
+  rc = m->tbl.ensure((size_t)g.grid * (size_t)(k->nodd + 1) * 4 * NTH * g.nthr * 16);
+  if (rc) return rc;
+  unsigned long long* ctr = nullptr;
+  rc = m->ctr.take(s, &ctr);
+  if (rc) return rc;
+  B body{k->d_enc_consts, cq, k->d_prog, k->nops, k->nodd, m_, r, c, batch, (u4*)m->tbl.p, ctr};
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
 }
 
@@ -591,6 +647,21 @@ int pai_pub_create(const uint32_t* n, int limbs, int device, pai_pub** out) {
   if (!rc) rc = rt_malloc((void**)&k->d_nth, (size_t)2 * ln * 4);
   if (!rc) rc = rt_h2d(k->d_nth, nn.data(), (size_t)ln * 4, 0);
   if (!rc) rc = rt_h2d(k->d_nth + ln, thr.data(), (size_t)ln * 4, 0);
+  // modulus n itself with the digit-form constants (encrypt runs on base-n digits, pai_digit.cuh)
+  if (!rc) rc = mod_create_impl(nn.data(), ln, device, 2 * ntp, dc_extra_limbs(2 * ntp), &k->nmod);
+  if (!rc) { DISPATCH_NTH(2 * ntp, rc = do_digit_setup<NTH>(k->nmod, 0)); }
+  if (!rc) {   // compact encrypt constants: [ N | ONE | NINV | KL | RR | ZERO ] gathered from the digit blob
+    const int h = 8 * 2 * ntp;
+    const uint32_t* b = k->nmod->d_blob;
+    const uint32_t* e = b + 5 * h + 8;            // KL | RR(2h) | ONEM(2h) | ZERO | ...
+    rc = rt_malloc((void**)&k->d_enc_consts, (size_t)dc_enc_limbs(2 * ntp) * 4);
+    uint32_t* c = k->d_enc_consts;
+    if (!rc) rc = rt_d2d(c, b, (size_t)h * 4, 0);                                  // N
+    if (!rc) rc = rt_d2d(c + h, b + 4 * h, (size_t)(h + 8) * 4, 0);                // ONE | NINV
+    if (!rc) rc = rt_d2d(c + 2 * h + 8, e, (size_t)3 * h * 4, 0);                  // KL | RR
+    if (!rc) rc = rt_d2d(c + 5 * h + 8, e + 5 * h, (size_t)h * 4, 0);              // ZERO
+  }
+  { const char* e = getenv("PAI_ENCRYPT_PATH"); k->use_digit = !(e && std::string(e) == "full"); }
   // exponent program for r^n: sliding windows of W_ENC bits over the public exponent n
   std::vector<uint32_t> prog = sliding_program(nn, W_ENC);
   k->nops = (int)prog.size();
@@ -607,8 +678,10 @@ int pai_pub_destroy(pai_pub* k) {
   if (k->nsq) rt_set_device(k->nsq->device);
   rt_free(k->d_nth);
   rt_free(k->d_prog);
+  rt_free(k->d_enc_consts);
   k->w_base.release(); k->w_exp.release(); k->w_flag.release(); k->h_m.release(); k->h_r.release(); k->h_c.release(); k->h_s.release();
   mod_free(k->nsq);
+  mod_free(k->nmod);
   delete k;
   return 0;
 }
@@ -620,7 +693,8 @@ int pai_encrypt(pai_pub* k, const uint32_t* d_m, const uint32_t* d_r, uint32_t* 
   if (batch == 0) return 0;
   int rc = rt_set_device(k->nsq->device);
   if (rc) return rc;
-  DISPATCH_NT(k->nsq->NT, rc = do_encrypt<NT>(k, d_m, d_r, d_c, batch, (rt_stream)stream));
+  if (k->use_digit) { DISPATCH_NTH(k->nmod->NT, rc = do_encrypt_digit<NTH>(k, d_m, d_r, d_c, batch, (rt_stream)stream)); }
+  else { DISPATCH_NT(k->nsq->NT, rc = do_encrypt<NT>(k, d_m, d_r, d_c, batch, (rt_stream)stream)); }
   return rc;
 }
 int pai_raw_add(pai_pub* k, const uint32_t* d_a, const uint32_t* d_b, uint32_t* d_c, long batch, void* stream) {

@@ -336,6 +336,32 @@ class EncryptedVector(object):
         c = limbs_to_ints(_to_host(limbs))[0]
         return EncryptedNumber(self.public_key, c, int(v.exponents[0]))
 
+    def dot(self, scalars):
+        """Homomorphic dot product sum_i self[i] * scalars[i] -> EncryptedNumber (the encrypted scoring loop of
+        examples/logistic_regression_encrypted_model.py:170-180 as two launches + a product tree)."""
+        return (self * scalars).sum()
+
+    # ------------------------------------------------------------------ wire format
+    def to_json(self, be_secure=True):
+        """The reference's basic JSON scheme (docs/serialisation.rst:24-31): {'public_key': {'n': ...},
+        'values': [[str(ciphertext), exponent], ...]} -- readable by an unmodified phe peer."""
+        import json
+        return json.dumps({"public_key": {"n": self.public_key.n},
+                           "values": [(str(c), int(e)) for c, e in zip(self.ciphertexts(be_secure), self.exponents)]})
+
+    @classmethod
+    def from_json(cls, serialised, public_key=None):
+        """Inverse of to_json (docs/serialisation.rst:35-42); ciphertexts go straight to the GPU."""
+        import json
+        from .paillier import PaillierPublicKey
+        d = json.loads(serialised)
+        pk = public_key or PaillierPublicKey(int(d["public_key"]["n"]))
+        if pk.n != int(d["public_key"]["n"]):
+            raise ValueError("serialised vector was encrypted against a different key")
+        ctx = pk.engine_context()
+        cts = [int(v[0]) % pk.nsquare for v in d["values"]]
+        return cls(pk, _to_dev(ints_to_limbs(cts, ctx.c_limbs), ctx), [int(v[1]) for v in d["values"]])
+
     # ------------------------------------------------------------------ decryption
     def decrypt_encoded(self, private_key):
         if self.public_key != private_key.public_key:

@@ -39,3 +39,32 @@ extern "C" void sim_tile(const uint32_t* a, const uint32_t* b, uint32_t* out16, 
   uint32_t v[8]; acc_resolve_low(A, v); memcpy(out16, v, 32); acc_shift8(A); acc_resolve_low(A, v); memcpy(out16 + 8, v, 32);
   mul_lo8(lo8, a, b);
 }
+
+#include "../../python-paillier_b200/csrc/pai_digit.cuh"
+template <int NTH>
+static void run_digit(int sqr, const uint32_t* x, const uint32_t* y, const uint32_t* N, const uint32_t* ninv, const uint32_t* KL, uint32_t* out) {
+  // x, y, out: 2*NTH tiles each as [d0 | d1]; simulate lane 1 of 3
+  const int nthr = 3, tid = 1, Q = 2 * NTH;               // quads per digit
+  std::vector<u4> X(2 * Q * nthr), Y(2 * Q * nthr), O(2 * Q * nthr), Nc(Q), NI(2), K(Q);
+  for (int q = 0; q < 2 * Q; q++) { memcpy(&X[q * nthr + tid], x + 4 * q, 16); memcpy(&Y[q * nthr + tid], y + 4 * q, 16); }
+  for (int q = 0; q < Q; q++) { memcpy(&Nc[q], N + 4 * q, 16); memcpy(&K[q], KL + 4 * q, 16); }
+  memcpy(NI.data(), ninv, 32);
+  Opnd bx{X.data() + tid, nthr}, by{Y.data() + tid, nthr}, bo{O.data() + tid, nthr};
+  Opnd oN{Nc.data(), 1}, oNI{NI.data(), 1}, oK{K.data(), 1};
+  if (sqr) dsqr<NTH>(half_lo<NTH>(bo), half_hi<NTH>(bo), half_lo<NTH>(bx), half_hi<NTH>(bx), oN, oNI, oK);
+  else dmul<NTH>(half_lo<NTH>(bo), half_hi<NTH>(bo), half_lo<NTH>(bx), half_hi<NTH>(bx), half_lo<NTH>(by), half_hi<NTH>(by), oN, oNI, oK);
+  // result: Z0 in hi half, Z1 in lo half -> return as [Z0 | Z1]
+  for (int q = 0; q < Q; q++) { memcpy(out + 4 * q, &O[(Q + q) * nthr + tid], 16); memcpy(out + 4 * (Q + q), &O[q * nthr + tid], 16); }
+}
+extern "C" int sim_digit(int NTH, int sqr, const uint32_t* x, const uint32_t* y, const uint32_t* N, const uint32_t* ninv, const uint32_t* KL, uint32_t* out) {
+  switch (NTH) {
+    case 1: run_digit<1>(sqr, x, y, N, ninv, KL, out); break;
+    case 2: run_digit<2>(sqr, x, y, N, ninv, KL, out); break;
+    case 3: run_digit<3>(sqr, x, y, N, ninv, KL, out); break;
+    case 4: run_digit<4>(sqr, x, y, N, ninv, KL, out); break;
+    case 8: run_digit<8>(sqr, x, y, N, ninv, KL, out); break;
+    case 12: run_digit<12>(sqr, x, y, N, ninv, KL, out); break;
+    default: return -1;
+  }
+  return 0;
+}

@@ -156,3 +156,39 @@ def test_dropin_api_and_vector_on_gpu(pkg, cuda_engine):
     assert sk.decrypt(acc.sum()) == pytest.approx(float(np.sum(grads)), abs=1e-9)
     lst = acc[:3].to_encrypted_numbers()
     assert [sk.decrypt(x) for x in lst] == sk.decrypt_batch(acc[:3])
+
+
+def test_streams_and_cuda_graph(pkg, cuda_engine, gmp):
+    """Device-pointer entry points are asynchronous on the caller's stream and capturable in a CUDA graph
+    (workspaces are sized by a warm-up call; nothing allocates or synchronises during capture)."""
+    import torch
+    kb, batch = 1024, 4096
+    n, p, q = _key(kb)
+    pub, priv = pkg.PublicContext(n), pkg.PrivateContext(p, q)
+    rng = np.random.default_rng(3)
+    m = _rand_rows(rng, batch, pub.n_limbs, kb // 32 - 1)
+    r = _rand_rows(rng, batch, pub.n_limbs, kb // 32 - 1)
+    r[:, 0] |= 1
+    d_m = torch.from_numpy(m.view(np.int32)).cuda()
+    d_r = torch.from_numpy(r.view(np.int32)).cuda()
+    d_c = torch.zeros((batch, pub.c_limbs), dtype=torch.int32, device="cuda")
+    d_d = torch.zeros((batch, pub.n_limbs), dtype=torch.int32, device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        pub.encrypt_dev(d_m, d_r, d_c, batch, stream=side.cuda_stream)          # warm-up on the side stream
+        priv.decrypt_dev(d_c, d_d, batch, stream=side.cuda_stream)
+    side.synchronize()
+    assert bool((d_d == d_m).all().item())
+    ref_c = d_c.clone()
+    d_c.zero_(); d_d.zero_()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        pub.encrypt_dev(d_m, d_r, d_c, batch, stream=side.cuda_stream)
+        priv.decrypt_dev(d_c, d_d, batch, stream=side.cuda_stream)
+    for _ in range(2):
+        d_c.zero_(); d_d.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert bool((d_c == ref_c).all().item()) and bool((d_d == d_m).all().item())

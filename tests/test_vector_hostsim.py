@@ -81,6 +81,16 @@ def test_vector_ops_match_scalar_semantics(pkg, env):
     assert s.ciphertexts(True) != c1 and sk.decrypt_batch(s) == [sk.decrypt(x + y) for x, y in zip(sa, sb)]
     back = pkg.EncryptedVector.from_encrypted_numbers(sa)
     assert back.ciphertexts(False) == va.ciphertexts(False) and len(back) == len(a)
+    assert sk.decrypt(va.dot(b)) == pytest.approx(sum(x * y for x, y in zip(a, b)), abs=1e-12)
+    # wire format of docs/serialisation.rst: readable with plain EncryptedNumber objects and back
+    import json
+    js = va.to_json(be_secure=False)
+    d = json.loads(js)
+    assert int(d["public_key"]["n"]) == pk.n
+    nums = [pkg.EncryptedNumber(pk, int(c), int(e)) for c, e in d["values"]]
+    assert [sk.decrypt(x) for x in nums] == sk.decrypt_batch(va)
+    rt = pkg.EncryptedVector.from_json(js)
+    assert rt.ciphertexts(False) == va.ciphertexts(False) and rt.exponents.tolist() == va.exponents.tolist()
     with pytest.raises(NotImplementedError):
         va * vb
     with pytest.raises(ValueError):
