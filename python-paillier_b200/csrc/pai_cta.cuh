@@ -256,4 +256,29 @@ PAI_DEV void cta_decrypt(u4* smem, const CtaId& id, int nwin_p, int nwin_q, cons
   }
 }
 
+
+// ---- decrypt in digit form.  consts = [ P side | Q side | pinvqM ], side = dside_limbs<NTP>() limbs
+template <int NTP>
+PAI_DEV int ddec_const_quads() { return 2 * (dside_limbs<NTP>() / 4) + 2 * NTP; }
+
+template <int NTP, int W>
+PAI_DEV void cta_decrypt_digit(u4* smem, const CtaId& id, int nwin_p, int nwin_q, const uint32_t* c, uint32_t* out, long batch,
+                               u4* tbl, unsigned long long* counter) {
+  DSideC<NTP> P, Qs;
+  dside_bind<NTP>(P, smem, nwin_p);
+  dside_bind<NTP>(Qs, smem + dside_limbs<NTP>() / 4, nwin_q);
+  Opnd pinvqM{smem + 2 * (dside_limbs<NTP>() / 4), 1};
+  DPowEnv<NTP> E;
+  cta_bufs<2 * NTP>(E.buf, 2, smem, ddec_const_quads<NTP>(), id);
+  E.tbl = cta_table_slots<2 * NTP>(tbl, id, 1 << W);
+  E.dc = &P.dc;
+  const int lc = 32 * NTP, ln = 16 * NTP;
+  RowSched sched = sched_init(id, counter, batch);
+  for (long g = sched_next_row(sched, id); g >= 0; g = sched_next_row(sched, id)) {
+    bool store = g < batch;
+    if (!store) g = batch - 1;
+    prog_decrypt_digit<NTP, W>(E, P, Qs, pinvqM, c + g * lc, out + g * ln, store);
+  }
+}
+
 }  // namespace pai

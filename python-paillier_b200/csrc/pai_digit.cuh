@@ -505,4 +505,166 @@ PAI_DEV void prog_encrypt_digit(const DPowEnv<NTH>& E, const uint32_t* prog, int
   if (store) store_row(out_row, E.buf[cur], 4 * NTH);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fixed-window exponentiation in digit form (secret exponent shared by the batch: decrypt's p-1 / q-1;
+// no digit is skipped).  Table: T[0] = 1, T[1] = base, T[i] = T[i-1]*base, 2^W entries in global memory.
+template <int NTH, int W>
+PAI_DEV int dpow_fixed(const DPowEnv<NTH>& E, int bi, int sw, const uint32_t* e, int nl, int nwin, int* sw_out) {
+  const DigitEnv& dc = *E.dc;
+  int cur = bi, oth = bi ^ 1;
+  if (nwin <= 0) {
+    DNum o = dview<NTH>(E.buf[oth], 0);
+    big_copy<NTH>(o.d0, dc.ONEM.d0);
+    big_copy<NTH>(o.d1, dc.ONEM.d1);
+    *sw_out = 0;
+    return oth;
+  }
+  DNum x = dview<NTH>(E.buf[cur], sw);
+  dtbl_store<NTH>(E, 0, dc.ONEM);
+  dtbl_store<NTH>(E, 1, x);
+  const DNum t1 = dtbl_entry<NTH>(E, 1);
+  dsqr<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, dc.N, dc.NI, dc.KL);
+  { int t = cur; cur = oth; oth = t; }
+  sw = 1;
+  dtbl_store<NTH>(E, 2, dview<NTH>(E.buf[cur], sw));
+  for (int i = 3; i < (1 << W); i++) {
+    x = dview<NTH>(E.buf[cur], sw);
+    dmul<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, t1.d0, t1.d1, dc.N, dc.NI, dc.KL);
+    { int t = cur; cur = oth; oth = t; }
+    dtbl_store<NTH>(E, i, dview<NTH>(E.buf[cur], sw));
+  }
+  {
+    const DNum t0 = dtbl_entry<NTH>(E, (int)exp_digit(e, nl, (nwin - 1) * W, W));
+    DNum c = dview<NTH>(E.buf[cur], 0);
+    big_copy<NTH>(c.d0, t0.d0);
+    big_copy<NTH>(c.d1, t0.d1);
+    sw = 0;
+  }
+  for (int wi = nwin - 2; wi >= 0; wi--) {
+    for (int s = 0; s < W; s++) {
+      x = dview<NTH>(E.buf[cur], sw);
+      dsqr<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, dc.N, dc.NI, dc.KL);
+      int t = cur; cur = oth; oth = t;
+      sw = 1;
+    }
+    x = dview<NTH>(E.buf[cur], sw);
+    const DNum te = dtbl_entry<NTH>(E, (int)exp_digit(e, nl, wi * W, W));
+    dmul<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, te.d0, te.d1, dc.N, dc.NI, dc.KL);
+    int t = cur; cur = oth; oth = t;
+    sw = 1;
+  }
+  *sw_out = sw;
+  return cur;
+}
+
+// a += b in digit form (canonical digits in, canonical digits out)
+template <int NTH>
+PAI_DEV void dadd(const DNum& a, const DNum& b, const Opnd& N) {
+  uint32_t c = big_add_masked<NTH>(a.d0, a.d0, b.d0, 0xffffffffu);
+  uint32_t carry = big_cond_sub<NTH>(a.d0, N, c);
+  // a.d1 = a.d1 + b.d1 + carry  (< 2n) then one conditional subtraction
+  uint32_t cc = carry;
+  for (int t = 0; t < NTH; t++) {
+    uint32_t x[8], y[8], r[8];
+    ld_tile(a.d1, t, x); ld_tile(b.d1, t, y);
+    cc = add8c(r, x, y, cc);
+    st_tile(a.d1, t, r);
+  }
+  big_cond_sub<NTH>(a.d1, N, cc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// raw_decrypt with CRT in digit form (phe/paillier.py:328-374).
+// One prime side x in {p, q}: constants = digit blob of x (digit_bind layout) followed by hM (h(x)*R mod x,
+// Montgomery form mod x) and the exponent x - 1.
+template <int NTP>
+struct DSideC {
+  DigitEnv dc;
+  Opnd R1;            // (unused placeholder for symmetry with the blob layout)
+  Opnd hM;
+  const uint32_t* e;
+  int nwin;
+};
+template <int NTP>
+PAI_HD int dside_limbs() { return dc_limbs(NTP) + 2 * 8 * NTP; }
+template <int NTP>
+PAI_DEV void dside_bind(DSideC<NTP>& S, u4* base, int nwin) {
+  digit_bind<NTP>(S.dc, base);
+  u4* p = base + dc_limbs(NTP) / 4;
+  S.hM.p = p; S.hM.s = 1;
+  S.R1 = S.hM;
+  S.e = (const uint32_t*)(p + 2 * NTP);
+  S.nwin = nwin;
+}
+
+// out: m_x = L(c^(x-1) mod x^2) * h mod x  (NTP tiles) in the LOW half of buf[ret]
+template <int NTP, int W>
+PAI_DEV int decrypt_half_digit(DPowEnv<NTP>& E, DSideC<NTP>& S, const uint32_t* c_row) {
+  DigitEnv& dc = S.dc;
+  E.dc = &dc;
+  const DNum Ek[4] = {dc.RR, dc.E3, dc.E4, dc.E5};
+  // X = c * R mod x^2:  c = sum_i c_i R^i (four pieces of NTP tiles, read from the global row)
+  Opnd c0{(u4*)c_row, 1};
+  dmul<NTP>(half_lo<NTP>(E.buf[0]), half_hi<NTP>(E.buf[0]), c0, dc.ZERO, Ek[0].d0, Ek[0].d1, dc.N, dc.NI, dc.KL);
+  for (int i = 1; i < 4; i++) {
+    Opnd ci{(u4*)(c_row + (size_t)i * 8 * NTP), 1};
+    dmul<NTP>(half_lo<NTP>(E.buf[1]), half_hi<NTP>(E.buf[1]), ci, dc.ZERO, Ek[i].d0, Ek[i].d1, dc.N, dc.NI, dc.KL);
+    dadd<NTP>(dview<NTP>(E.buf[0], 1), dview<NTP>(E.buf[1], 1), dc.N);
+  }
+  int sw = 1;
+  int cur = dpow_fixed<NTP, W>(E, 0, 1, S.e, 8 * NTP, S.nwin, &sw);      // c^(x-1) * R mod x^2
+  int oth = cur ^ 1;
+  DNum x = dview<NTP>(E.buf[cur], sw);
+  dmul<NTP>(half_lo<NTP>(E.buf[oth]), half_hi<NTP>(E.buf[oth]), x.d0, x.d1, dc.ONE, dc.ZERO, dc.N, dc.NI, dc.KL);
+  // plain digits u = u0 + x*u1:  L(u) = (u-1)//x = u1 if u0 >= 1;  u0 == 0: u1 - 1, and -1 = x - 1 (mod x) if u1 == 0
+  DNum u = dview<NTP>(E.buf[oth], 1);
+  uint32_t u0z = big_is_zero<NTP>(u.d0);
+  uint32_t u1z = big_is_zero<NTP>(u.d1);
+  big_sub_masked<NTP>(u.d1, u.d1, dc.ONE, 0u - (u0z & (u1z ^ 1u)));
+  {
+    const uint32_t sel = u0z & u1z;
+    for (int t = 0; t < NTP; t++) {
+      uint32_t l[8], n[8];
+      ld_tile(u.d1, t, l); ld_tile(dc.N, t, n);
+      if (t == 0) n[0] -= 1u;                                             // x is odd: no borrow
+      PAI_UNROLL
+      for (int i = 0; i < 8; i++) l[i] = sel ? n[i] : l[i];
+      st_tile(u.d1, t, l);
+    }
+  }
+  mont_mul<NTP>(half_lo<NTP>(E.buf[cur]), u.d1, S.hM, dc.N, dc.NI);        // L * h mod x
+  return cur;
+}
+
+template <int NTP, int W>
+PAI_DEV void prog_decrypt_digit(DPowEnv<NTP>& E, DSideC<NTP>& P, DSideC<NTP>& Qs, const Opnd& pinvqM,
+                                const uint32_t* c_row, uint32_t* out_row, bool store) {
+  int ip = decrypt_half_digit<NTP, W>(E, P, c_row);
+  if (store) store_row(out_row, half_lo<NTP>(E.buf[ip]), 2 * NTP);        // m_p -> global (low half of the row)
+  int c = decrypt_half_digit<NTP, W>(E, Qs, c_row);
+  int o = c ^ 1;
+  Opnd mq = half_lo<NTP>(E.buf[c]), mp = half_hi<NTP>(E.buf[c]);
+  if (store) load_row(mp, out_row, 2 * NTP, 2 * NTP);
+  else big_copy<NTP>(mp, mq);
+  // u = (m_q - m_p) * p^-1 mod q     (m_p < p < q, m_q < q)
+  uint32_t bo = big_sub_masked<NTP>(mq, mq, mp, 0xffffffffu);
+  big_add_masked<NTP>(mq, mq, Qs.dc.N, 0u - bo);
+  Opnd uo = half_lo<NTP>(E.buf[o]), mp2 = half_hi<NTP>(E.buf[o]);
+  mont_mul<NTP>(uo, mq, pinvqM, Qs.dc.N, Qs.dc.NI);
+  big_copy<NTP>(mp2, mp);
+  // m = m_p + u * p
+  big_mul<NTP, NTP, 2 * NTP>(E.buf[c], uo, P.dc.N, 0u);
+  uint32_t cy = 0;
+  for (int t = 0; t < 2 * NTP; t++) {
+    uint32_t a[8], b[8], r[8];
+    ld_tile(E.buf[c], t, a);
+    if (t < NTP) ld_tile(mp2, t, b);
+    else { PAI_UNROLL for (int i = 0; i < 8; i++) b[i] = 0; }
+    cy = add8c(r, a, b, cy);
+    st_tile(E.buf[c], t, r);
+  }
+  if (store) store_row(out_row, E.buf[c], 4 * NTP);
+}
+
 }  // namespace pai

@@ -85,6 +85,12 @@ struct DecBody {
   int nwin_p, nwin_q; const uint32_t* c; uint32_t* out; long batch; u4* tbl; unsigned long long* counter;
   PAI_MEM void run(u4* smem, const CtaId& id) const { cta_decrypt<NTP, W>(smem, id, nwin_p, nwin_q, c, out, batch, tbl, counter); }
 };
+template <int NTP, int W>
+struct DecDigitBody {
+  const uint32_t* consts; int const_quads;
+  int nwin_p, nwin_q; const uint32_t* c; uint32_t* out; long batch; u4* tbl; unsigned long long* counter;
+  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_decrypt_digit<NTP, W>(smem, id, nwin_p, nwin_q, c, out, batch, tbl, counter); }
+};
 // one CRT half with h = 1 (used once per key to derive hp / hq): out = L(g^(x-1) mod x^2) mod x
 template <int NTP, int W>
 struct LBody {
@@ -274,7 +280,10 @@ struct pai_pub {
 struct pai_priv {
   int device = 0, NTP = 0;
   pai_mod *p2 = nullptr, *q2 = nullptr, *p1 = nullptr, *q1 = nullptr;
-  uint32_t* d_consts = nullptr;     // [ P side | Q side | pinvqM ]
+  uint32_t* d_consts = nullptr;     // [ P side | Q side | pinvqM ]  (full-width path, also used to derive hp/hq)
+  pai_mod *pd = nullptr, *qd = nullptr;   // p, q with digit-form constants (pai_digit.cuh)
+  uint32_t* d_dconsts = nullptr;    // digit path: [ P: dblob(p) | hM | e ][ Q: ... ][ pinvqM ]
+  bool use_digit = true;
   int nwin_p = 0, nwin_q = 0;
   limbs_t h_p, h_q, h_pinv, h_hp, h_hq;   // 16*NTP limbs each (padded)
   DevBuf tbl, h_c, h_m;
@@ -461,6 +470,58 @@ int do_decrypt(pai_priv* k, const uint32_t* c, uint32_t* out, long batch, rt_str
   if (rc) return rc;
   B body{k->d_consts, cq, k->nwin_p, k->nwin_q, c, out, batch, (u4*)k->tbl.p, ctr};
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
+}
+
+template <int NTP>
+int do_decrypt_digit(pai_priv* k, const uint32_t* c, uint32_t* out, long batch, rt_stream s) {
+  typedef DecDigitBody<NTP, W_DEC> B;
+  Geom g;
+  int cq = 2 * (dside_limbs<NTP>() / 4) + 2 * NTP;
+  int rc = geometry<B>(k->device, 2 * NTP, cq, 2, batch, g);
+  if (rc) return rc;
+  rc = k->tbl.ensure((size_t)g.grid * ((size_t)1 << W_DEC) * 4 * NTP * g.nthr * 16);
+  if (rc) return rc;
+  unsigned long long* ctr = nullptr;
+  rc = k->ctr.take(s, &ctr);
+  if (rc) return rc;
+  B body{k->d_dconsts, cq, k->nwin_p, k->nwin_q, c, out, batch, (u4*)k->tbl.p, ctr};
+  return rt_launch(body, g.grid, g.nthr, g.smem, s);
+}
+
+// digit-form constants of the private key, assembled from the digit blobs of p and q and from the
+// h / exponent / p^-1 constants the full-width setup has already derived.
+template <int NTP>
+int do_priv_digit_setup(pai_priv* k, rt_stream s) {
+  const int L1 = 8 * NTP;
+  int rc = mod_create_impl(k->h_p.data(), L1, k->device, NTP, dc_extra_limbs(NTP), &k->pd);
+  if (!rc) rc = mod_create_impl(k->h_q.data(), L1, k->device, NTP, dc_extra_limbs(NTP), &k->qd);
+  if (rc) return rc;
+  for (pai_mod* m : {k->pd, k->qd}) {
+    void* scratch = nullptr;
+    rc = rt_malloc(&scratch, (size_t)4 * L1 * 4);
+    if (rc) return rc;
+    DigitSetupBody<NTP> b{nullptr, 0, m->d_blob, (uint32_t*)scratch};
+    rc = rt_launch(b, 1, 32, 0, s);
+    if (!rc) rc = rt_sync(s);
+    rt_free(scratch);
+    if (rc) return rc;
+  }
+  const int side = dside_limbs<NTP>();
+  size_t total = ((size_t)2 * side + L1) * 4;
+  rc = rt_malloc((void**)&k->d_dconsts, total);
+  if (rc) return rc;
+  const int old_side = mc_limbs(2 * NTP) + mc_limbs(NTP) + 3 * L1;     // [ blob(x^2) | blob(x) | xinv | hM | e ]
+  const int old_hM = mc_limbs(2 * NTP) + mc_limbs(NTP) + L1;
+  pai_mod* md[2] = {k->pd, k->qd};
+  for (int i = 0; i < 2 && !rc; i++) {
+    uint32_t* dst = k->d_dconsts + (size_t)i * side;
+    const uint32_t* old = k->d_consts + (size_t)i * old_side;
+    rc = rt_d2d(dst, md[i]->d_blob, (size_t)dc_limbs(NTP) * 4, s);
+    if (!rc) rc = rt_d2d(dst + dc_limbs(NTP), old + old_hM, (size_t)2 * L1 * 4, s);      // hM | e
+  }
+  if (!rc) rc = rt_d2d(k->d_dconsts + (size_t)2 * side, k->d_consts + (size_t)2 * old_side, (size_t)L1 * 4, s);   // pinvqM
+  if (!rc) rc = rt_sync(s);
+  return rc;
 }
 
 // derive one side's constants on the device.  side layout: [ blob(x^2) | blob(x) | xinv | hM | e ]
@@ -749,6 +810,8 @@ int pai_priv_create(const uint32_t* p, const uint32_t* q, int limbs, int device,
   if (!rc) rc = mod_create_impl(pp.data(), L1, device, ntp, 0, &k->p1);
   if (!rc) rc = mod_create_impl(qq.data(), L1, device, ntp, 0, &k->q1);
   if (!rc) { DISPATCH_NTP(ntp, rc = do_priv_setup<NTP>(k, 0)); }
+  if (!rc) { DISPATCH_NTP(ntp, rc = do_priv_digit_setup<NTP>(k, 0)); }
+  { const char* e = getenv("PAI_DECRYPT_PATH"); k->use_digit = !(e && std::string(e) == "full"); }
   if (rc) { pai_priv_destroy(k); return rc; }
   *out = k;
   return 0;
@@ -762,6 +825,13 @@ int pai_priv_destroy(pai_priv* k) {
     rt_sync(0);
   }
   rt_free(k->d_consts);
+  if (k->d_dconsts) {
+    const int L1 = 8 * k->NTP;
+    rt_memset(k->d_dconsts, 0, ((size_t)2 * (5 * L1 + 8 + 12 * L1 + 2 * L1) + L1) * 4, 0);
+    rt_sync(0);
+  }
+  rt_free(k->d_dconsts);
+  mod_free(k->pd); mod_free(k->qd);
   k->ctr.buf.release(); k->tbl.release(); k->h_c.release(); k->h_m.release();
   mod_free(k->p2); mod_free(k->q2); mod_free(k->p1); mod_free(k->q1);
   std::fill(k->h_p.begin(), k->h_p.end(), 0); std::fill(k->h_q.begin(), k->h_q.end(), 0);
@@ -787,7 +857,8 @@ int pai_decrypt(pai_priv* k, const uint32_t* d_c, uint32_t* d_m, long batch, voi
   if (batch == 0) return 0;
   int rc = rt_set_device(k->device);
   if (rc) return rc;
-  DISPATCH_NTP(k->NTP, rc = do_decrypt<NTP>(k, d_c, d_m, batch, (rt_stream)stream));
+  if (k->use_digit) { DISPATCH_NTP(k->NTP, rc = do_decrypt_digit<NTP>(k, d_c, d_m, batch, (rt_stream)stream)); }
+  else { DISPATCH_NTP(k->NTP, rc = do_decrypt<NTP>(k, d_c, d_m, batch, (rt_stream)stream)); }
   return rc;
 }
 
