@@ -31,14 +31,14 @@ DEFAULT_BATCH = 1 << 20
 
 
 def executed_macs_2048():
-    """MACs the kernels actually execute per op at 2048-bit keys (tile counts of pai_core.cuh: 64 MACs per tile
-    product, 36 for the truncated quotient product): sliding-window encrypt and fixed-window CRT decrypt."""
-    def mul(nt):
-        return 64 * (2 * nt * nt) + 36 * nt
-    def sqr(nt):
-        return 64 * (nt * (nt - 1) // 2 + nt + nt * nt) + 36 * nt
-    enc = 2048 * sqr(16) + (293 + 32 + 2) * mul(16)          # ~2048 squarings, ~293 window + 31 table multiplications
-    dec = 2 * (1024 * sqr(8) + (205 + 30 + 4) * mul(8))
+    """MACs the kernels actually execute per op at 2048-bit keys on the base-n digit path (pai_digit.cuh): 64 MACs
+    per tile product, 36 per truncated quotient product; sliding-window encrypt (w = 6), fixed-window CRT decrypt."""
+    def dmul(nth):
+        return 64 * (5 * nth * nth + 2 * nth) + 36 * 2 * nth
+    def dsqr(nth):
+        return 64 * (nth * (nth - 1) // 2 + nth + nth * nth + nth + 2 * nth * nth + nth) + 36 * 2 * nth
+    enc = 2048 * dsqr(8) + (293 + 32 + 2) * dmul(8) + 64 * 64
+    dec = 2 * (1024 * dsqr(4) + (205 + 30 + 6) * dmul(4))
     return enc, dec
 
 
@@ -347,7 +347,7 @@ def main():
     peak_mac_s = peak["mac_per_clk_sm"] * 148 * sm_mhz * 1e6
     ach_mac_s = enc_per_s / world * mac_enc
     roofline = {
-        "bound": "int_pipe", "kernel": "k_body<EncBody<16>> (raw_encrypt, r^n mod n^2)",
+        "bound": "int_pipe", "kernel": "k_body<EncDigitBody<8>> (raw_encrypt, r^n mod n^2 on base-n digits)",
         "achieved": ach_mac_s / 1e12, "peak": peak_mac_s / 1e12, "unit": "TMAC/s (32x32->64, canonical count, per GPU)",
         "frac": ach_mac_s / peak_mac_s,
         "note": "canonical MAC counts (SURVEY 8d) give no credit for squaring / sliding windows, so frac may exceed 1; "

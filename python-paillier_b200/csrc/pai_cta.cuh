@@ -281,4 +281,29 @@ PAI_DEV void cta_decrypt_digit(u4* smem, const CtaId& id, int nwin_p, int nwin_q
   }
 }
 
+
+// ---- c^k mod n^2 in digit form (raw_mul).  consts = compact constants with ONEM and E3 (dc_pow_limbs)
+template <int NTH, int W>
+PAI_DEV void cta_powmod_digit(u4* smem, const CtaId& id, const uint32_t* base, const uint32_t* exp, int exp_limbs, uint32_t* out,
+                              long batch, u4* tbl, unsigned long long* counter) {
+  DigitEnv dc;
+  digit_bind_pow<NTH>(dc, smem);
+  DPowEnv<NTH> E;
+  cta_bufs<2 * NTH>(E.buf, 2, smem, dc_pow_limbs(NTH) / 4, id);
+  E.tbl = cta_table_slots<2 * NTH>(tbl, id, 1 << W);
+  E.dc = &dc;
+  const int lc = 16 * NTH;
+  RowSched sched = sched_init(id, counter, batch);
+  for (long g = sched_next_row(sched, id); g >= 0; g = sched_next_row(sched, id)) {
+    bool store = g < batch;
+    if (!store) g = batch - 1;
+    const uint32_t* e = exp + g * exp_limbs;
+    int nwin = (limbs_bitlen(e, exp_limbs) + W - 1) / W;
+#if !defined(PAI_HOSTSIM)
+    nwin = __reduce_max_sync(0xffffffffu, nwin);
+#endif
+    prog_powmod_digit<NTH, W>(E, base + g * lc, e, exp_limbs, nwin, out + g * lc, store);
+  }
+}
+
 }  // namespace pai

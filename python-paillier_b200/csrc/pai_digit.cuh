@@ -318,6 +318,8 @@ PAI_DEV void digit_bind(DigitEnv& d, u4* blob) {
 // 1 KB of operands still fit the 227 KB of shared memory at 2048-bit keys):
 //   [ N (h) | ONE (h) | NINV (8) | KL (h) | RR (2h) | ZERO (h) ]
 PAI_HD int dc_enc_limbs(int NTH) { return 8 * NTH * 6 + 8; }
+// the scalar-multiplication kernel appends [ ONEM (2h) | E3 (2h) ] to the same prefix
+PAI_HD int dc_pow_limbs(int NTH) { return 8 * NTH * 10 + 8; }
 template <int NTH>
 PAI_DEV void digit_bind_enc(DigitEnv& d, u4* c) {
   const int Q = 2 * NTH;
@@ -329,6 +331,15 @@ PAI_DEV void digit_bind_enc(DigitEnv& d, u4* c) {
   d.RR.d1.p = c + 4 * Q + 2;  d.RR.d1.s = 1;
   d.ZERO.p = c + 5 * Q + 2;   d.ZERO.s = 1;
   d.ONEM = d.RR; d.E3 = d.RR; d.E4 = d.RR; d.E5 = d.RR;      // not used by encrypt
+}
+template <int NTH>
+PAI_DEV void digit_bind_pow(DigitEnv& d, u4* c) {
+  const int Q = 2 * NTH;
+  digit_bind_enc<NTH>(d, c);
+  d.ONEM.d0.p = c + 6 * Q + 2;  d.ONEM.d0.s = 1;
+  d.ONEM.d1.p = c + 7 * Q + 2;  d.ONEM.d1.s = 1;
+  d.E3.d0.p = c + 8 * Q + 2;    d.E3.d0.s = 1;
+  d.E3.d1.p = c + 9 * Q + 2;    d.E3.d1.s = 1;
 }
 
 // single-thread setup of the extra constants; blob(n) (N, R1, ..., NINV) must already be set up.
@@ -665,6 +676,27 @@ PAI_DEV void prog_decrypt_digit(DPowEnv<NTP>& E, DSideC<NTP>& P, DSideC<NTP>& Qs
     st_tile(E.buf[c], t, r);
   }
   if (store) store_row(out_row, E.buf[c], 4 * NTP);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// c^k mod n^2 with per-element exponents in digit form (EncryptedNumber._raw_mul, phe/paillier.py:749-751).
+//   base row: plain ciphertext, 2*NTH tiles = c_0 + c_1*R;  e: exponent limbs of this element; nwin uniform.
+template <int NTH, int W>
+PAI_DEV void prog_powmod_digit(DPowEnv<NTH>& E, const uint32_t* base_row, const uint32_t* e, int nl, int nwin,
+                               uint32_t* out_row, bool store) {
+  const DigitEnv& dc = *E.dc;
+  Opnd c0{(u4*)base_row, 1}, c1{(u4*)(base_row + 8 * NTH), 1};
+  dmul<NTH>(half_lo<NTH>(E.buf[0]), half_hi<NTH>(E.buf[0]), c0, dc.ZERO, dc.RR.d0, dc.RR.d1, dc.N, dc.NI, dc.KL);
+  dmul<NTH>(half_lo<NTH>(E.buf[1]), half_hi<NTH>(E.buf[1]), c1, dc.ZERO, dc.E3.d0, dc.E3.d1, dc.N, dc.NI, dc.KL);
+  dadd<NTH>(dview<NTH>(E.buf[0], 1), dview<NTH>(E.buf[1], 1), dc.N);
+  int sw = 1;
+  int cur = dpow_fixed<NTH, W>(E, 0, 1, e, nl, nwin, &sw);
+  int oth = cur ^ 1;
+  DNum x = dview<NTH>(E.buf[cur], sw);
+  dmul<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, dc.ONE, dc.ZERO, dc.N, dc.NI, dc.KL);
+  digits_to_plain<NTH>(E.buf[cur], dview<NTH>(E.buf[oth], 1), dc.N);
+  if (store) store_row(out_row, E.buf[cur], 4 * NTH);
 }
 
 }  // namespace pai

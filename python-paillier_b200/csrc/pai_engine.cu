@@ -51,6 +51,12 @@ struct EncDigitBody {
   unsigned long long* counter;
   PAI_MEM void run(u4* smem, const CtaId& id) const { cta_encrypt_digit<NTH>(smem, id, prog, nops, nodd, m, r, out, batch, tbl, counter); }
 };
+template <int NTH, int W>
+struct PowDigitBody {
+  const uint32_t* consts; int const_quads;
+  const uint32_t* base; const uint32_t* exp; int exp_limbs; uint32_t* out; long batch; u4* tbl; unsigned long long* counter;
+  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_powmod_digit<NTH, W>(smem, id, base, exp, exp_limbs, out, batch, tbl, counter); }
+};
 template <int NT>
 struct MulBody {
   const uint32_t* consts; int const_quads;
@@ -456,6 +462,23 @@ int do_encrypt_digit(pai_pub* k, const uint32_t* m_, const uint32_t* r, uint32_t
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
 }
 
+template <int NTH>
+int do_powmod_digit(pai_pub* k, const uint32_t* base, const uint32_t* d_exp, int exp_limbs, uint32_t* out, long batch, rt_stream s) {
+  typedef PowDigitBody<NTH, W_VAR> B;
+  pai_mod* m = k->nmod;
+  Geom g;
+  int cq = dc_pow_limbs(NTH) / 4;
+  int rc = geometry<B>(m->device, 2 * NTH, cq, 2, batch, g);
+  if (rc) return rc;
+  rc = m->tbl.ensure((size_t)g.grid * ((size_t)1 << W_VAR) * 4 * NTH * g.nthr * 16);
+  if (rc) return rc;
+  unsigned long long* ctr = nullptr;
+  rc = m->ctr.take(s, &ctr);
+  if (rc) return rc;
+  B body{k->d_enc_consts, cq, base, d_exp, exp_limbs, out, batch, (u4*)m->tbl.p, ctr};
+  return rt_launch(body, g.grid, g.nthr, g.smem, s);
+}
+
 template <int NTP>
 int do_decrypt(pai_priv* k, const uint32_t* c, uint32_t* out, long batch, rt_stream s) {
   typedef DecBody<NTP, W_DEC> B;
@@ -715,12 +738,14 @@ int pai_pub_create(const uint32_t* n, int limbs, int device, pai_pub** out) {
     const int h = 8 * 2 * ntp;
     const uint32_t* b = k->nmod->d_blob;
     const uint32_t* e = b + 5 * h + 8;            // KL | RR(2h) | ONEM(2h) | ZERO | ...
-    rc = rt_malloc((void**)&k->d_enc_consts, (size_t)dc_enc_limbs(2 * ntp) * 4);
+    rc = rt_malloc((void**)&k->d_enc_consts, (size_t)dc_pow_limbs(2 * ntp) * 4);
     uint32_t* c = k->d_enc_consts;
     if (!rc) rc = rt_d2d(c, b, (size_t)h * 4, 0);                                  // N
     if (!rc) rc = rt_d2d(c + h, b + 4 * h, (size_t)(h + 8) * 4, 0);                // ONE | NINV
     if (!rc) rc = rt_d2d(c + 2 * h + 8, e, (size_t)3 * h * 4, 0);                  // KL | RR
     if (!rc) rc = rt_d2d(c + 5 * h + 8, e + 5 * h, (size_t)h * 4, 0);              // ZERO
+    if (!rc) rc = rt_d2d(c + 6 * h + 8, e + 3 * h, (size_t)2 * h * 4, 0);          // ONEM
+    if (!rc) rc = rt_d2d(c + 8 * h + 8, e + 6 * h, (size_t)2 * h * 4, 0);          // E3
   }
   { const char* e = getenv("PAI_ENCRYPT_PATH"); k->use_digit = !(e && std::string(e) == "full"); }
   // exponent program for r^n: sliding windows of W_ENC bits over the public exponent n
@@ -786,6 +811,10 @@ int pai_raw_mul(pai_pub* k, const uint32_t* d_a, const uint32_t* d_s, uint32_t* 
   DISPATCH_NT(m->NT, rc = do_invert<NT>(m, d_a, lc / 8, flag, (uint32_t*)k->w_base.p, status, batch, s));
   if (rc) return rc;
   // 3. base ^ exponent mod n^2
+  if (k->use_digit) {
+    DISPATCH_NTH(k->nmod->NT, rc = do_powmod_digit<NTH>(k, (const uint32_t*)k->w_base.p, (const uint32_t*)k->w_exp.p, ln, d_c, batch, s));
+    return rc;
+  }
   return powmod_common(m, (const uint32_t*)k->w_base.p, lc, (const uint32_t*)k->w_exp.p, ln, ln, -1, d_c, batch, stream);
 }
 
