@@ -479,6 +479,7 @@ template <int NT>
 PAI_FN void mont_mul(Opnd out, Opnd a, Opnd b, Opnd N, Opnd NI) {
   Acc acc;
   acc_clear(acc);
+  uint32_t bo = 0;
   uint32_t n0[8], ninv[8];
   ld_tile(N, 0, n0);
   ld_tile(NI, 0, ninv);
@@ -506,11 +507,15 @@ PAI_FN void mont_mul(Opnd out, Opnd a, Opnd b, Opnd N, Opnd NI) {
     } else {
       acc_resolve_low(acc, v);
       st_tile(out, k - NT, v);
+      uint32_t nt[8], d[8];
+      ld_tile(N, k - NT, nt);
+      bo = sub8b(d, v, nt, bo);                  // running borrow of (result - N): no separate compare pass
     }
     acc_shift8(acc);
   }
   uint32_t ovf = lo32(acc.E[0]) + acc.C[0];   // what is left is 0 or 1, in column 0
-  big_cond_sub<NT>(out, N, ovf);
+  uint32_t need = (ovf != 0u) | (bo ^ 1u);
+  big_sub_masked<NT>(out, out, N, 0u - need);
 }
 
 // Montgomery squaring: out = a*a/R mod N.  Off-diagonal tile products are accumulated once in a
@@ -524,7 +529,7 @@ PAI_FN void mont_sqr(Opnd out, Opnd a, Opnd N, Opnd NI) {
   uint32_t n0[8], ninv[8];
   ld_tile(N, 0, n0);
   ld_tile(NI, 0, ninv);
-  uint32_t topbit = 0;
+  uint32_t topbit = 0, bo = 0;
   for (int k = 0; k < 2 * NT; k++) {
     int lo = k - NT + 1 > 0 ? k - NT + 1 : 0;
     int hi = k < NT ? k - 1 : NT - 1;
@@ -574,11 +579,15 @@ PAI_FN void mont_sqr(Opnd out, Opnd a, Opnd N, Opnd NI) {
     } else {
       acc_resolve_low(acc, v);
       st_tile(out, k - NT, v);
+      uint32_t nt[8], d[8];
+      ld_tile(N, k - NT, nt);
+      bo = sub8b(d, v, nt, bo);
     }
     acc_shift8(acc);
   }
   uint32_t ovf = lo32(acc.E[0]) + acc.C[0] + topbit;
-  big_cond_sub<NT>(out, N, ovf);
+  uint32_t need = (ovf != 0u) | (bo ^ 1u);
+  big_sub_masked<NT>(out, out, N, 0u - need);
 }
 
 }  // namespace pai

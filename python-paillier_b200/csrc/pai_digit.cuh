@@ -41,7 +41,13 @@ PAI_DEV Opnd half_hi(const Opnd& b) {
   return o;
 }
 
-// broadcast constants of one digit modulus n
+struct DigitEnv {
+  Opnd N, NI, KL, ONE, ZERO;
+  Opnd N2, N3, TOPS;          // 2n mod R, 3n mod R, and their overflow words (TOPS tile: [top2, top3, ...])
+  DNum RR, ONEM, E3, E4, E5;
+};
+
+// (legacy descriptor, kept for documentation of the constants)
 struct DigitC {
   Opnd N, NI;      // n, tile holding -n^-1 mod 2^256
   Opnd KL;         // n - (R mod n):  K = R + KL is the multiple of n used to keep phase 2 non-negative
@@ -77,8 +83,23 @@ PAI_DEV void big_reduce_small(const Opnd& x, const Opnd& N, uint32_t ovf) {
 // Z = X * Y * R^-1 mod n^2 in digit form.  Output: Z0 in ohi, Z1 in olo (the two halves of one buffer, or any
 // two disjoint NTH-tile regions that alias none of the inputs).  X0 may be any value < R if Y0 < n (and
 // vice versa); X1, Y1 may be any values < R.
+// Reduction of the second phase: V = olo + ovf*R < 3n + 2.  b1, b2, b3 are the borrows of olo - (c*n mod R)
+// gathered while the result tiles were produced; q = #{c : V >= c*n}; one masked subtraction of q*n.
 template <int NTH>
-PAI_FN void dmul(Opnd olo, Opnd ohi, Opnd x0, Opnd x1, Opnd y0, Opnd y1, Opnd N, Opnd NI, Opnd KL) {
+PAI_DEV void digit_reduce3(const Opnd& olo, const DigitEnv& dc, uint32_t ovf, uint32_t b1, uint32_t b2, uint32_t b3) {
+  const u4 tops = dc.TOPS.p[0];
+  const int s1 = (int)ovf - (int)b1;
+  const int s2 = (int)ovf - (int)tops.x - (int)b2;
+  const int s3 = (int)ovf - (int)tops.y - (int)b3;
+  const int q = (s1 >= 0) + (s2 >= 0) + (s3 >= 0);
+  Opnd sel = q == 2 ? dc.N2 : (q == 3 ? dc.N3 : dc.N);
+  big_sub_masked<NTH>(olo, olo, sel, q ? 0xffffffffu : 0u);
+}
+
+template <int NTH>
+PAI_FN void dmul(Opnd olo, Opnd ohi, Opnd x0, Opnd x1, Opnd y0, Opnd y1, const DigitEnv* dcp) {
+  const DigitEnv& dc = *dcp;
+  const Opnd N = dc.N, NI = dc.NI, KL = dc.KL;
   uint32_t n0[8], ninv[8];
   ld_tile(N, 0, n0);
   ld_tile(NI, 0, ninv);
@@ -87,6 +108,7 @@ PAI_FN void dmul(Opnd olo, Opnd ohi, Opnd x0, Opnd x1, Opnd y0, Opnd y1, Opnd N,
   {
     Acc acc;
     acc_clear(acc);
+    uint32_t b1 = 0;
     for (int k = 0; k < 2 * NTH; k++) {
       int lo = k - NTH + 1 > 0 ? k - NTH + 1 : 0;
       int hi = k < NTH ? k - 1 : NTH - 1;
@@ -110,11 +132,15 @@ PAI_FN void dmul(Opnd olo, Opnd ohi, Opnd x0, Opnd x1, Opnd y0, Opnd y1, Opnd N,
       } else {
         acc_resolve_low(acc, v);
         st_tile(ohi, k - NTH, v);
+        uint32_t nt[8], d[8];
+        ld_tile(N, k - NTH, nt);
+        b1 = sub8b(d, v, nt, b1);
       }
       acc_shift8(acc);
     }
     uint32_t ovf = lo32(acc.E[0]) + acc.C[0];
-    carry = big_cond_sub<NTH>(ohi, N, ovf);
+    carry = (ovf != 0u) | (b1 ^ 1u);
+    big_sub_masked<NTH>(ohi, ohi, N, 0u - carry);
   }
   // ---- W = (R + KL) - m  >= 0:  low NTH tiles in olo, top part wtop.  Reducing the low digit by n carries
   // +1 into the high digit; adding R to B adds exactly 1 to REDC_n(B), so the carry rides on wtop.
@@ -123,6 +149,7 @@ PAI_FN void dmul(Opnd olo, Opnd ohi, Opnd x0, Opnd x1, Opnd y0, Opnd y1, Opnd N,
   {
     Acc acc;
     acc_clear(acc);
+    uint32_t b1 = 0, b2 = 0, b3 = 0;
     for (int k = 0; k < 2 * NTH; k++) {
       int lo = k - NTH + 1 > 0 ? k - NTH + 1 : 0;
       int hi = k < NTH ? k - 1 : NTH - 1;
@@ -153,17 +180,23 @@ PAI_FN void dmul(Opnd olo, Opnd ohi, Opnd x0, Opnd x1, Opnd y0, Opnd y1, Opnd N,
         if (k == NTH) acc.C[0] += wtop;
         acc_resolve_low(acc, v);
         st_tile(olo, k - NTH, v);
+        uint32_t nt[8], d[8];
+        ld_tile(N, k - NTH, nt);      b1 = sub8b(d, v, nt, b1);
+        ld_tile(dc.N2, k - NTH, nt);  b2 = sub8b(d, v, nt, b2);
+        ld_tile(dc.N3, k - NTH, nt);  b3 = sub8b(d, v, nt, b3);
       }
       acc_shift8(acc);
     }
     uint32_t ovf = lo32(acc.E[0]) + acc.C[0];
-    big_reduce_small<NTH, 3>(olo, N, ovf);
+    digit_reduce3<NTH>(olo, dc, ovf, b1, b2, b3);
   }
 }
 
 // Z = X^2 * R^-1 mod n^2 in digit form (X0, X1 canonical).  Output as in dmul.
 template <int NTH>
-PAI_FN void dsqr(Opnd olo, Opnd ohi, Opnd x0, Opnd x1, Opnd N, Opnd NI, Opnd KL) {
+PAI_FN void dsqr(Opnd olo, Opnd ohi, Opnd x0, Opnd x1, const DigitEnv* dcp) {
+  const DigitEnv& dc = *dcp;
+  const Opnd N = dc.N, NI = dc.NI, KL = dc.KL;
   uint32_t n0[8], ninv[8];
   ld_tile(N, 0, n0);
   ld_tile(NI, 0, ninv);
@@ -173,7 +206,7 @@ PAI_FN void dsqr(Opnd olo, Opnd ohi, Opnd x0, Opnd x1, Opnd N, Opnd NI, Opnd KL)
     Acc acc, S;
     acc_clear(acc);
     acc_clear(S);
-    uint32_t topbit = 0;
+    uint32_t topbit = 0, b1 = 0;
     for (int k = 0; k < 2 * NTH; k++) {
       int lo = k - NTH + 1 > 0 ? k - NTH + 1 : 0;
       int hi = k < NTH ? k - 1 : NTH - 1;
@@ -217,11 +250,15 @@ PAI_FN void dsqr(Opnd olo, Opnd ohi, Opnd x0, Opnd x1, Opnd N, Opnd NI, Opnd KL)
       } else {
         acc_resolve_low(acc, v);
         st_tile(ohi, k - NTH, v);
+        uint32_t nt[8], d[8];
+        ld_tile(N, k - NTH, nt);
+        b1 = sub8b(d, v, nt, b1);
       }
       acc_shift8(acc);
     }
     uint32_t ovf = lo32(acc.E[0]) + acc.C[0] + topbit;
-    carry = big_cond_sub<NTH>(ohi, N, ovf);
+    carry = (ovf != 0u) | (b1 ^ 1u);
+    big_sub_masked<NTH>(ohi, ohi, N, 0u - carry);
   }
   uint32_t wtop = 1u - big_rsub<NTH>(olo, KL) + carry;
   // ---- phase 2: B = 2*x0*x1 + W  (all NTH^2 cross tiles once in S, doubled on the way in)
@@ -229,7 +266,7 @@ PAI_FN void dsqr(Opnd olo, Opnd ohi, Opnd x0, Opnd x1, Opnd N, Opnd NI, Opnd KL)
     Acc acc, S;
     acc_clear(acc);
     acc_clear(S);
-    uint32_t topbit = 0;
+    uint32_t topbit = 0, b1 = 0, b2 = 0, b3 = 0;
     for (int k = 0; k < 2 * NTH; k++) {
       int lo = k - NTH + 1 > 0 ? k - NTH + 1 : 0;
       int hi = k < NTH ? k - 1 : NTH - 1;            // reduction partners i in [lo, hi]; cross tiles i in [lo, hc]
@@ -271,27 +308,28 @@ PAI_FN void dsqr(Opnd olo, Opnd ohi, Opnd x0, Opnd x1, Opnd N, Opnd NI, Opnd KL)
         if (k == NTH) acc.C[0] += wtop;
         acc_resolve_low(acc, v);
         st_tile(olo, k - NTH, v);
+        uint32_t nt[8], d[8];
+        ld_tile(N, k - NTH, nt);      b1 = sub8b(d, v, nt, b1);
+        ld_tile(dc.N2, k - NTH, nt);  b2 = sub8b(d, v, nt, b2);
+        ld_tile(dc.N3, k - NTH, nt);  b3 = sub8b(d, v, nt, b3);
       }
       acc_shift8(acc);
     }
     uint32_t ovf = lo32(acc.E[0]) + acc.C[0] + topbit;
-    big_reduce_small<NTH, 3>(olo, N, ovf);
+    digit_reduce3<NTH>(olo, dc, ovf, b1, b2, b3);
   }
 }
 
 
 // ------------------------------------------------------------------------------------------------
 // Constants blob of one digit modulus (uint32 limbs, h = 8*NTH), appended to the ordinary blob of n:
-//   [ blob(n): N | R1 | R2 | R3 | ONE | NINV(8) ]  [ KL (h) | RR (2h) | ONEM (2h) | ZERO (h) | E3 (2h) | E4 (2h) | E5 (2h) ]
+//   [ blob(n): N | R1 | R2 | R3 | ONE | NINV(8) ]  [ KL (h) | RR (2h) | ONEM (2h) | ZERO (h) | E3 (2h) | E4 (2h) | E5 (2h) | N2 (h) | N3 (h) | TOPS (8) ]
 // RR = digits of R^2 mod n^2, ONEM = digits of R mod n^2, Ek = digits of R^k mod n^2 (entry constants for
 // double-width inputs: c = sum c_i R^i  ->  c*R = sum dmul((c_i, 0), E(i+2))).
-PAI_HD int dc_extra_limbs(int NTH) { return 8 * NTH * (1 + 2 + 2 + 1 + 2 + 2 + 2); }
+PAI_HD int dc_extra_limbs(int NTH) { return 8 * NTH * (1 + 2 + 2 + 1 + 2 + 2 + 2 + 1 + 1) + 8; }
 PAI_HD int dc_limbs(int NTH) { return 5 * 8 * NTH + 8 + dc_extra_limbs(NTH); }
 
-struct DigitEnv {
-  Opnd N, NI, KL, ONE, ZERO;
-  DNum RR, ONEM, E3, E4, E5;
-};
+
 
 template <int NTH>
 PAI_DEV void digit_bind(DigitEnv& d, u4* blob) {
@@ -312,14 +350,17 @@ PAI_DEV void digit_bind(DigitEnv& d, u4* blob) {
   d.E4.d1.p = e + 9 * Q;      d.E4.d1.s = 1;
   d.E5.d0.p = e + 10 * Q;     d.E5.d0.s = 1;
   d.E5.d1.p = e + 11 * Q;     d.E5.d1.s = 1;
+  d.N2.p = e + 12 * Q;        d.N2.s = 1;
+  d.N3.p = e + 13 * Q;        d.N3.s = 1;
+  d.TOPS.p = e + 14 * Q;      d.TOPS.s = 1;
 }
 
 // Compact constant area of the encrypt kernel (only what prog_encrypt_digit touches, so that 224 threads x
 // 1 KB of operands still fit the 227 KB of shared memory at 2048-bit keys):
-//   [ N (h) | ONE (h) | NINV (8) | KL (h) | RR (2h) | ZERO (h) ]
-PAI_HD int dc_enc_limbs(int NTH) { return 8 * NTH * 6 + 8; }
+//   [ N (h) | ONE (h) | NINV (8) | KL (h) | RR (2h) | ZERO (h) | N2 (h) | N3 (h) | TOPS (8) ]
+PAI_HD int dc_enc_limbs(int NTH) { return 8 * NTH * 8 + 16; }
 // the scalar-multiplication kernel appends [ ONEM (2h) | E3 (2h) ] to the same prefix
-PAI_HD int dc_pow_limbs(int NTH) { return 8 * NTH * 10 + 8; }
+PAI_HD int dc_pow_limbs(int NTH) { return 8 * NTH * 12 + 16; }
 template <int NTH>
 PAI_DEV void digit_bind_enc(DigitEnv& d, u4* c) {
   const int Q = 2 * NTH;
@@ -330,16 +371,19 @@ PAI_DEV void digit_bind_enc(DigitEnv& d, u4* c) {
   d.RR.d0.p = c + 3 * Q + 2;  d.RR.d0.s = 1;
   d.RR.d1.p = c + 4 * Q + 2;  d.RR.d1.s = 1;
   d.ZERO.p = c + 5 * Q + 2;   d.ZERO.s = 1;
+  d.N2.p = c + 6 * Q + 2;     d.N2.s = 1;
+  d.N3.p = c + 7 * Q + 2;     d.N3.s = 1;
+  d.TOPS.p = c + 8 * Q + 2;   d.TOPS.s = 1;
   d.ONEM = d.RR; d.E3 = d.RR; d.E4 = d.RR; d.E5 = d.RR;      // not used by encrypt
 }
 template <int NTH>
 PAI_DEV void digit_bind_pow(DigitEnv& d, u4* c) {
   const int Q = 2 * NTH;
   digit_bind_enc<NTH>(d, c);
-  d.ONEM.d0.p = c + 6 * Q + 2;  d.ONEM.d0.s = 1;
-  d.ONEM.d1.p = c + 7 * Q + 2;  d.ONEM.d1.s = 1;
-  d.E3.d0.p = c + 8 * Q + 2;    d.E3.d0.s = 1;
-  d.E3.d1.p = c + 9 * Q + 2;    d.E3.d1.s = 1;
+  d.ONEM.d0.p = c + 8 * Q + 4;  d.ONEM.d0.s = 1;
+  d.ONEM.d1.p = c + 9 * Q + 4;  d.ONEM.d1.s = 1;
+  d.E3.d0.p = c + 10 * Q + 4;   d.E3.d0.s = 1;
+  d.E3.d1.p = c + 11 * Q + 4;   d.E3.d1.s = 1;
 }
 
 // single-thread setup of the extra constants; blob(n) (N, R1, ..., NINV) must already be set up.
@@ -385,13 +429,27 @@ PAI_DEV void digit_setup(uint32_t* blob, uint32_t* scratch) {
   }
   for (int i = 0; i < h; i++) { RR[i] = d0[i]; RR[h + i] = d1[i]; }
   // E3 = RR*RR/R = R^3, E4 = E3*RR/R, E5 = E4*RR/R   (digit Montgomery products, stride-1 operands)
-  Opnd oN{(u4*)blob, 1}, oNI{(u4*)(blob + 5 * h), 1}, oKL{(u4*)KL, 1};
+  // N2 = 2n mod R, N3 = 3n mod R and their overflow words
+  uint32_t* N2 = e + 12 * h;
+  uint32_t* N3 = e + 13 * h;
+  uint32_t* TOPS = e + 14 * h;
+  {
+    uint64_t c = 0;
+    for (int i = 0; i < h; i++) { c += 2ull * N[i]; N2[i] = (uint32_t)c; c >>= 32; }
+    TOPS[0] = (uint32_t)c;
+    c = 0;
+    for (int i = 0; i < h; i++) { c += 3ull * N[i]; N3[i] = (uint32_t)c; c >>= 32; }
+    TOPS[1] = (uint32_t)c;
+    for (int i = 2; i < 8; i++) TOPS[i] = 0;
+  }
+  DigitEnv env;
+  digit_bind<NTH>(env, (u4*)blob);
   Opnd r0{(u4*)RR, 1}, r1{(u4*)(RR + h), 1};
   Opnd tmp{(u4*)scratch, 1};                                  // 2h limbs: lo | hi
   uint32_t* Es[3] = {E3, E4, E5};
   Opnd p0 = r0, p1 = r1;
   for (int k = 0; k < 3; k++) {
-    dmul<NTH>(half_lo<NTH>(tmp), half_hi<NTH>(tmp), p0, p1, r0, r1, oN, oNI, oKL);
+    dmul<NTH>(half_lo<NTH>(tmp), half_hi<NTH>(tmp), p0, p1, r0, r1, &env);
     for (int i = 0; i < h; i++) { Es[k][i] = scratch[h + i]; Es[k][h + i] = scratch[i]; }     // (Z0 = hi, Z1 = lo)
     p0.p = (u4*)Es[k]; p1.p = (u4*)(Es[k] + h);
   }
@@ -444,12 +502,12 @@ PAI_DEV int dpow_prog(const DPowEnv<NTH>& E, int bi, int sw, const uint32_t* pro
   DNum x = dview<NTH>(E.buf[cur], sw);
   dtbl_store<NTH>(E, 0, x);                                               // T[0] = base
   if (nodd > 1) {
-    dsqr<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, dc.N, dc.NI, dc.KL);
+    dsqr<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, &dc);
     dtbl_store<NTH>(E, nodd, dview<NTH>(E.buf[oth], 1));                  // base^2
     const DNum b2 = dtbl_entry<NTH>(E, nodd);
     for (int k = 1; k < nodd; k++) {                                      // T[k] = T[k-1] * base^2
       x = dview<NTH>(E.buf[cur], sw);
-      dmul<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, b2.d0, b2.d1, dc.N, dc.NI, dc.KL);
+      dmul<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, b2.d0, b2.d1, &dc);
       { int t = cur; cur = oth; oth = t; }
       sw = 1;
       dtbl_store<NTH>(E, k, dview<NTH>(E.buf[cur], sw));
@@ -467,14 +525,14 @@ PAI_DEV int dpow_prog(const DPowEnv<NTH>& E, int bi, int sw, const uint32_t* pro
     const int nsq = (int)(op >> 16), idx = (int)(op & 0xffffu);
     for (int s = 0; s < nsq; s++) {
       x = dview<NTH>(E.buf[cur], sw);
-      dsqr<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, dc.N, dc.NI, dc.KL);
+      dsqr<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, &dc);
       int t = cur; cur = oth; oth = t;
       sw = 1;
     }
     if (idx != 0xffff) {
       x = dview<NTH>(E.buf[cur], sw);
       const DNum te = dtbl_entry<NTH>(E, idx);
-      dmul<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, te.d0, te.d1, dc.N, dc.NI, dc.KL);
+      dmul<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, te.d0, te.d1, &dc);
       int t = cur; cur = oth; oth = t;
       sw = 1;
     }
@@ -506,12 +564,12 @@ PAI_DEV void prog_encrypt_digit(const DPowEnv<NTH>& E, const uint32_t* prog, int
                                 const uint32_t* m_row, const uint32_t* r_row, uint32_t* out_row, bool store) {
   const DigitEnv& dc = *E.dc;
   Opnd r_op{(u4*)r_row, 1}, m_op{(u4*)m_row, 1};
-  dmul<NTH>(half_lo<NTH>(E.buf[0]), half_hi<NTH>(E.buf[0]), r_op, dc.ZERO, dc.RR.d0, dc.RR.d1, dc.N, dc.NI, dc.KL);
+  dmul<NTH>(half_lo<NTH>(E.buf[0]), half_hi<NTH>(E.buf[0]), r_op, dc.ZERO, dc.RR.d0, dc.RR.d1, &dc);
   int sw = 1;
   int cur = dpow_prog<NTH>(E, 0, 1, prog, nops, nodd, &sw);
   int oth = cur ^ 1;
   DNum x = dview<NTH>(E.buf[cur], sw);
-  dmul<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, dc.ONE, m_op, dc.N, dc.NI, dc.KL);
+  dmul<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, dc.ONE, m_op, &dc);
   digits_to_plain<NTH>(E.buf[cur], dview<NTH>(E.buf[oth], 1), dc.N);
   if (store) store_row(out_row, E.buf[cur], 4 * NTH);
 }
@@ -535,13 +593,13 @@ PAI_DEV int dpow_fixed(const DPowEnv<NTH>& E, int bi, int sw, const uint32_t* e,
   dtbl_store<NTH>(E, 0, dc.ONEM);
   dtbl_store<NTH>(E, 1, x);
   const DNum t1 = dtbl_entry<NTH>(E, 1);
-  dsqr<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, dc.N, dc.NI, dc.KL);
+  dsqr<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, &dc);
   { int t = cur; cur = oth; oth = t; }
   sw = 1;
   dtbl_store<NTH>(E, 2, dview<NTH>(E.buf[cur], sw));
   for (int i = 3; i < (1 << W); i++) {
     x = dview<NTH>(E.buf[cur], sw);
-    dmul<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, t1.d0, t1.d1, dc.N, dc.NI, dc.KL);
+    dmul<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, t1.d0, t1.d1, &dc);
     { int t = cur; cur = oth; oth = t; }
     dtbl_store<NTH>(E, i, dview<NTH>(E.buf[cur], sw));
   }
@@ -555,13 +613,13 @@ PAI_DEV int dpow_fixed(const DPowEnv<NTH>& E, int bi, int sw, const uint32_t* e,
   for (int wi = nwin - 2; wi >= 0; wi--) {
     for (int s = 0; s < W; s++) {
       x = dview<NTH>(E.buf[cur], sw);
-      dsqr<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, dc.N, dc.NI, dc.KL);
+      dsqr<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, &dc);
       int t = cur; cur = oth; oth = t;
       sw = 1;
     }
     x = dview<NTH>(E.buf[cur], sw);
     const DNum te = dtbl_entry<NTH>(E, (int)exp_digit(e, nl, wi * W, W));
-    dmul<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, te.d0, te.d1, dc.N, dc.NI, dc.KL);
+    dmul<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, te.d0, te.d1, &dc);
     int t = cur; cur = oth; oth = t;
     sw = 1;
   }
@@ -617,17 +675,17 @@ PAI_DEV int decrypt_half_digit(DPowEnv<NTP>& E, DSideC<NTP>& S, const uint32_t* 
   const DNum Ek[4] = {dc.RR, dc.E3, dc.E4, dc.E5};
   // X = c * R mod x^2:  c = sum_i c_i R^i (four pieces of NTP tiles, read from the global row)
   Opnd c0{(u4*)c_row, 1};
-  dmul<NTP>(half_lo<NTP>(E.buf[0]), half_hi<NTP>(E.buf[0]), c0, dc.ZERO, Ek[0].d0, Ek[0].d1, dc.N, dc.NI, dc.KL);
+  dmul<NTP>(half_lo<NTP>(E.buf[0]), half_hi<NTP>(E.buf[0]), c0, dc.ZERO, Ek[0].d0, Ek[0].d1, &dc);
   for (int i = 1; i < 4; i++) {
     Opnd ci{(u4*)(c_row + (size_t)i * 8 * NTP), 1};
-    dmul<NTP>(half_lo<NTP>(E.buf[1]), half_hi<NTP>(E.buf[1]), ci, dc.ZERO, Ek[i].d0, Ek[i].d1, dc.N, dc.NI, dc.KL);
+    dmul<NTP>(half_lo<NTP>(E.buf[1]), half_hi<NTP>(E.buf[1]), ci, dc.ZERO, Ek[i].d0, Ek[i].d1, &dc);
     dadd<NTP>(dview<NTP>(E.buf[0], 1), dview<NTP>(E.buf[1], 1), dc.N);
   }
   int sw = 1;
   int cur = dpow_fixed<NTP, W>(E, 0, 1, S.e, 8 * NTP, S.nwin, &sw);      // c^(x-1) * R mod x^2
   int oth = cur ^ 1;
   DNum x = dview<NTP>(E.buf[cur], sw);
-  dmul<NTP>(half_lo<NTP>(E.buf[oth]), half_hi<NTP>(E.buf[oth]), x.d0, x.d1, dc.ONE, dc.ZERO, dc.N, dc.NI, dc.KL);
+  dmul<NTP>(half_lo<NTP>(E.buf[oth]), half_hi<NTP>(E.buf[oth]), x.d0, x.d1, dc.ONE, dc.ZERO, &dc);
   // plain digits u = u0 + x*u1:  L(u) = (u-1)//x = u1 if u0 >= 1;  u0 == 0: u1 - 1, and -1 = x - 1 (mod x) if u1 == 0
   DNum u = dview<NTP>(E.buf[oth], 1);
   uint32_t u0z = big_is_zero<NTP>(u.d0);
@@ -687,14 +745,14 @@ PAI_DEV void prog_powmod_digit(DPowEnv<NTH>& E, const uint32_t* base_row, const 
                                uint32_t* out_row, bool store) {
   const DigitEnv& dc = *E.dc;
   Opnd c0{(u4*)base_row, 1}, c1{(u4*)(base_row + 8 * NTH), 1};
-  dmul<NTH>(half_lo<NTH>(E.buf[0]), half_hi<NTH>(E.buf[0]), c0, dc.ZERO, dc.RR.d0, dc.RR.d1, dc.N, dc.NI, dc.KL);
-  dmul<NTH>(half_lo<NTH>(E.buf[1]), half_hi<NTH>(E.buf[1]), c1, dc.ZERO, dc.E3.d0, dc.E3.d1, dc.N, dc.NI, dc.KL);
+  dmul<NTH>(half_lo<NTH>(E.buf[0]), half_hi<NTH>(E.buf[0]), c0, dc.ZERO, dc.RR.d0, dc.RR.d1, &dc);
+  dmul<NTH>(half_lo<NTH>(E.buf[1]), half_hi<NTH>(E.buf[1]), c1, dc.ZERO, dc.E3.d0, dc.E3.d1, &dc);
   dadd<NTH>(dview<NTH>(E.buf[0], 1), dview<NTH>(E.buf[1], 1), dc.N);
   int sw = 1;
   int cur = dpow_fixed<NTH, W>(E, 0, 1, e, nl, nwin, &sw);
   int oth = cur ^ 1;
   DNum x = dview<NTH>(E.buf[cur], sw);
-  dmul<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, dc.ONE, dc.ZERO, dc.N, dc.NI, dc.KL);
+  dmul<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, dc.ONE, dc.ZERO, &dc);
   digits_to_plain<NTH>(E.buf[cur], dview<NTH>(E.buf[oth], 1), dc.N);
   if (store) store_row(out_row, E.buf[cur], 4 * NTH);
 }

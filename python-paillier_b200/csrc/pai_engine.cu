@@ -744,8 +744,9 @@ int pai_pub_create(const uint32_t* n, int limbs, int device, pai_pub** out) {
     if (!rc) rc = rt_d2d(c + h, b + 4 * h, (size_t)(h + 8) * 4, 0);                // ONE | NINV
     if (!rc) rc = rt_d2d(c + 2 * h + 8, e, (size_t)3 * h * 4, 0);                  // KL | RR
     if (!rc) rc = rt_d2d(c + 5 * h + 8, e + 5 * h, (size_t)h * 4, 0);              // ZERO
-    if (!rc) rc = rt_d2d(c + 6 * h + 8, e + 3 * h, (size_t)2 * h * 4, 0);          // ONEM
-    if (!rc) rc = rt_d2d(c + 8 * h + 8, e + 6 * h, (size_t)2 * h * 4, 0);          // E3
+    if (!rc) rc = rt_d2d(c + 6 * h + 8, e + 12 * h, (size_t)(2 * h + 8) * 4, 0);   // N2 | N3 | TOPS
+    if (!rc) rc = rt_d2d(c + 8 * h + 16, e + 3 * h, (size_t)2 * h * 4, 0);         // ONEM
+    if (!rc) rc = rt_d2d(c + 10 * h + 16, e + 6 * h, (size_t)2 * h * 4, 0);        // E3
   }
   { const char* e = getenv("PAI_ENCRYPT_PATH"); k->use_digit = !(e && std::string(e) == "full"); }
   // exponent program for r^n: sliding windows of W_ENC bits over the public exponent n
@@ -856,7 +857,7 @@ int pai_priv_destroy(pai_priv* k) {
   rt_free(k->d_consts);
   if (k->d_dconsts) {
     const int L1 = 8 * k->NTP;
-    rt_memset(k->d_dconsts, 0, ((size_t)2 * (5 * L1 + 8 + 12 * L1 + 2 * L1) + L1) * 4, 0);
+    rt_memset(k->d_dconsts, 0, ((size_t)2 * (5 * L1 + 8 + 14 * L1 + 8 + 2 * L1) + L1) * 4, 0);
     rt_sync(0);
   }
   rt_free(k->d_dconsts);

@@ -51,8 +51,19 @@ static void run_digit(int sqr, const uint32_t* x, const uint32_t* y, const uint3
   memcpy(NI.data(), ninv, 32);
   Opnd bx{X.data() + tid, nthr}, by{Y.data() + tid, nthr}, bo{O.data() + tid, nthr};
   Opnd oN{Nc.data(), 1}, oNI{NI.data(), 1}, oK{K.data(), 1};
-  if (sqr) dsqr<NTH>(half_lo<NTH>(bo), half_hi<NTH>(bo), half_lo<NTH>(bx), half_hi<NTH>(bx), oN, oNI, oK);
-  else dmul<NTH>(half_lo<NTH>(bo), half_hi<NTH>(bo), half_lo<NTH>(bx), half_hi<NTH>(bx), half_lo<NTH>(by), half_hi<NTH>(by), oN, oNI, oK);
+  std::vector<u4> N2v(Q), N3v(Q), TOPv(2);
+  {
+    const uint32_t* n32 = (const uint32_t*)Nc.data();
+    uint32_t* a2 = (uint32_t*)N2v.data(); uint32_t* a3 = (uint32_t*)N3v.data(); uint32_t* tp = (uint32_t*)TOPv.data();
+    uint64_t c = 0; for (int i = 0; i < 8 * NTH; i++) { c += 2ull * n32[i]; a2[i] = (uint32_t)c; c >>= 32; } tp[0] = (uint32_t)c;
+    c = 0; for (int i = 0; i < 8 * NTH; i++) { c += 3ull * n32[i]; a3[i] = (uint32_t)c; c >>= 32; } tp[1] = (uint32_t)c;
+    for (int i = 2; i < 8; i++) tp[i] = 0;
+  }
+  DigitEnv env;
+  env.N = oN; env.NI = oNI; env.KL = oK; env.ONE = oN; env.ZERO = oN;
+  env.N2 = Opnd{N2v.data(), 1}; env.N3 = Opnd{N3v.data(), 1}; env.TOPS = Opnd{TOPv.data(), 1};
+  if (sqr) dsqr<NTH>(half_lo<NTH>(bo), half_hi<NTH>(bo), half_lo<NTH>(bx), half_hi<NTH>(bx), &env);
+  else dmul<NTH>(half_lo<NTH>(bo), half_hi<NTH>(bo), half_lo<NTH>(bx), half_hi<NTH>(bx), half_lo<NTH>(by), half_hi<NTH>(by), &env);
   // result: Z0 in hi half, Z1 in lo half -> return as [Z0 | Z1]
   for (int q = 0; q < Q; q++) { memcpy(out + 4 * q, &O[(Q + q) * nthr + tid], 16); memcpy(out + 4 * (Q + q), &O[q * nthr + tid], 16); }
 }
