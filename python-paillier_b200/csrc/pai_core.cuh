@@ -254,6 +254,14 @@ PAI_DEV void acc_peek_low(const Acc& A, uint32_t v[8]) {
   add8(v, t, A.C);
 }
 
+// The low 8 limbs of the accumulator VALUE are known to be 0 mod 2^256 (right after acc += m * n0 in a
+// Montgomery step): their carry into limb 8 is k = (E + O + C at limb 7, + 2) >> 32 -- the limbs below 7 sum to
+// delta * 2^224 with delta in {0, 1, 2}, so limb 7 holds k*2^32 - delta.  Replaces two 8-limb carry chains.
+PAI_DEV void acc_carry_of_zero_low(Acc& A) {
+  uint64_t s7 = (uint64_t)hi32(A.E[3]) + lo32(A.O[3]) + A.C[7] + 2u;
+  A.C[8] += (uint32_t)(s7 >> 32);
+}
+
 // A.low8 += d[0..7]  (carry captured in C[8])
 PAI_DEV void acc_add_low(Acc& A, const uint32_t d[8]) {
   uint32_t e[8], t[8];
@@ -503,7 +511,7 @@ PAI_FN void mont_mul(Opnd out, Opnd a, Opnd b, Opnd N, Opnd NI) {
       mul_lo8(m, v, ninv);
       st_tile(out, k, m);
       tile_mac(acc, m, n0);
-      acc_resolve_low(acc, v);          // == 0 by construction; pushes the carry into C[8]
+      acc_carry_of_zero_low(acc);       // low tile == 0 by construction; its carry goes to C[8]
     } else {
       acc_resolve_low(acc, v);
       st_tile(out, k - NT, v);
@@ -575,7 +583,7 @@ PAI_FN void mont_sqr(Opnd out, Opnd a, Opnd N, Opnd NI) {
       mul_lo8(m, v, ninv);
       st_tile(out, k, m);
       tile_mac(acc, m, n0);
-      acc_resolve_low(acc, v);
+      acc_carry_of_zero_low(acc);
     } else {
       acc_resolve_low(acc, v);
       st_tile(out, k - NT, v);

@@ -111,9 +111,10 @@ PAI_DEV void cta_encrypt(u4* smem, const CtaId& id, const uint32_t* prog, int no
 // 2*NTH tiles per thread; r and m are read straight from their global rows.
 template <int NTH>
 PAI_DEV void cta_encrypt_digit(u4* smem, const CtaId& id, const uint32_t* prog, int nops, int nodd, const uint32_t* m,
-                               const uint32_t* r, uint32_t* out, long batch, u4* tbl, unsigned long long* counter) {
+                               const uint32_t* r, uint32_t* out, long batch, u4* tbl, unsigned long long* counter,
+                               const uint32_t* gzero) {
   DigitEnv dc;
-  digit_bind_enc<NTH>(dc, smem);
+  digit_bind_enc<NTH>(dc, smem, gzero);
   DPowEnv<NTH> E;
   cta_bufs<2 * NTH>(E.buf, 2, smem, dc_enc_limbs(NTH) / 4, id);
   E.tbl = cta_table_slots<2 * NTH>(tbl, id, nodd + 1);
@@ -285,9 +286,9 @@ PAI_DEV void cta_decrypt_digit(u4* smem, const CtaId& id, int nwin_p, int nwin_q
 // ---- c^k mod n^2 in digit form (raw_mul).  consts = compact constants with ONEM and E3 (dc_pow_limbs)
 template <int NTH, int W>
 PAI_DEV void cta_powmod_digit(u4* smem, const CtaId& id, const uint32_t* base, const uint32_t* exp, int exp_limbs, uint32_t* out,
-                              long batch, u4* tbl, unsigned long long* counter) {
+                              long batch, u4* tbl, unsigned long long* counter, const uint32_t* gzero) {
   DigitEnv dc;
-  digit_bind_pow<NTH>(dc, smem);
+  digit_bind_pow<NTH>(dc, smem, gzero);
   DPowEnv<NTH> E;
   cta_bufs<2 * NTH>(E.buf, 2, smem, dc_pow_limbs(NTH) / 4, id);
   E.tbl = cta_table_slots<2 * NTH>(tbl, id, 1 << W);

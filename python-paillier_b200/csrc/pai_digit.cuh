@@ -128,7 +128,7 @@ PAI_FN void dmul(Opnd olo, Opnd ohi, Opnd x0, Opnd x1, Opnd y0, Opnd y1, const D
         mul_lo8(m, v, ninv);
         st_tile(olo, k, m);
         tile_mac(acc, m, n0);
-        acc_resolve_low(acc, v);
+        acc_carry_of_zero_low(acc);
       } else {
         acc_resolve_low(acc, v);
         st_tile(ohi, k - NTH, v);
@@ -175,7 +175,7 @@ PAI_FN void dmul(Opnd olo, Opnd ohi, Opnd x0, Opnd x1, Opnd y0, Opnd y1, const D
         mul_lo8(m, v, ninv);
         st_tile(olo, k, m);
         tile_mac(acc, m, n0);
-        acc_resolve_low(acc, v);
+        acc_carry_of_zero_low(acc);
       } else {
         if (k == NTH) acc.C[0] += wtop;
         acc_resolve_low(acc, v);
@@ -246,7 +246,7 @@ PAI_FN void dsqr(Opnd olo, Opnd ohi, Opnd x0, Opnd x1, const DigitEnv* dcp) {
         mul_lo8(m, v, ninv);
         st_tile(olo, k, m);
         tile_mac(acc, m, n0);
-        acc_resolve_low(acc, v);
+        acc_carry_of_zero_low(acc);
       } else {
         acc_resolve_low(acc, v);
         st_tile(ohi, k - NTH, v);
@@ -303,7 +303,7 @@ PAI_FN void dsqr(Opnd olo, Opnd ohi, Opnd x0, Opnd x1, const DigitEnv* dcp) {
         mul_lo8(m, v, ninv);
         st_tile(olo, k, m);
         tile_mac(acc, m, n0);
-        acc_resolve_low(acc, v);
+        acc_carry_of_zero_low(acc);
       } else {
         if (k == NTH) acc.C[0] += wtop;
         acc_resolve_low(acc, v);
@@ -357,12 +357,15 @@ PAI_DEV void digit_bind(DigitEnv& d, u4* blob) {
 
 // Compact constant area of the encrypt kernel (only what prog_encrypt_digit touches, so that 224 threads x
 // 1 KB of operands still fit the 227 KB of shared memory at 2048-bit keys):
-//   [ N (h) | ONE (h) | NINV (8) | KL (h) | RR (2h) | ZERO (h) | N2 (h) | N3 (h) | TOPS (8) ]
-PAI_HD int dc_enc_limbs(int NTH) { return 8 * NTH * 8 + 16; }
+//   [ N (h) | ONE (h) | NINV (8) | KL (h) | RR (2h) | N2 (h) | N3 (h) | TOPS (8) ]
+// (the all-zero operand is read from the global digit blob: it is only touched when entering/leaving the domain)
+PAI_HD int dc_enc_limbs(int NTH) { return 8 * NTH * 7 + 16; }
 // the scalar-multiplication kernel appends [ ONEM (2h) | E3 (2h) ] to the same prefix
-PAI_HD int dc_pow_limbs(int NTH) { return 8 * NTH * 12 + 16; }
+PAI_HD int dc_pow_limbs(int NTH) { return 8 * NTH * 11 + 16; }
+// offset (limbs) of the ZERO region inside the global digit blob
+PAI_HD int dc_zero_offset(int NTH) { return 5 * 8 * NTH + 8 + 5 * 8 * NTH; }
 template <int NTH>
-PAI_DEV void digit_bind_enc(DigitEnv& d, u4* c) {
+PAI_DEV void digit_bind_enc(DigitEnv& d, u4* c, const uint32_t* gzero) {
   const int Q = 2 * NTH;
   d.N.p = c;                  d.N.s = 1;
   d.ONE.p = c + Q;            d.ONE.s = 1;
@@ -370,20 +373,20 @@ PAI_DEV void digit_bind_enc(DigitEnv& d, u4* c) {
   d.KL.p = c + 2 * Q + 2;     d.KL.s = 1;
   d.RR.d0.p = c + 3 * Q + 2;  d.RR.d0.s = 1;
   d.RR.d1.p = c + 4 * Q + 2;  d.RR.d1.s = 1;
-  d.ZERO.p = c + 5 * Q + 2;   d.ZERO.s = 1;
-  d.N2.p = c + 6 * Q + 2;     d.N2.s = 1;
-  d.N3.p = c + 7 * Q + 2;     d.N3.s = 1;
-  d.TOPS.p = c + 8 * Q + 2;   d.TOPS.s = 1;
+  d.ZERO.p = (u4*)gzero;      d.ZERO.s = 1;
+  d.N2.p = c + 5 * Q + 2;     d.N2.s = 1;
+  d.N3.p = c + 6 * Q + 2;     d.N3.s = 1;
+  d.TOPS.p = c + 7 * Q + 2;   d.TOPS.s = 1;
   d.ONEM = d.RR; d.E3 = d.RR; d.E4 = d.RR; d.E5 = d.RR;      // not used by encrypt
 }
 template <int NTH>
-PAI_DEV void digit_bind_pow(DigitEnv& d, u4* c) {
+PAI_DEV void digit_bind_pow(DigitEnv& d, u4* c, const uint32_t* gzero) {
   const int Q = 2 * NTH;
-  digit_bind_enc<NTH>(d, c);
-  d.ONEM.d0.p = c + 8 * Q + 4;  d.ONEM.d0.s = 1;
-  d.ONEM.d1.p = c + 9 * Q + 4;  d.ONEM.d1.s = 1;
-  d.E3.d0.p = c + 10 * Q + 4;   d.E3.d0.s = 1;
-  d.E3.d1.p = c + 11 * Q + 4;   d.E3.d1.s = 1;
+  digit_bind_enc<NTH>(d, c, gzero);
+  d.ONEM.d0.p = c + 7 * Q + 4;  d.ONEM.d0.s = 1;
+  d.ONEM.d1.p = c + 8 * Q + 4;  d.ONEM.d1.s = 1;
+  d.E3.d0.p = c + 9 * Q + 4;    d.E3.d0.s = 1;
+  d.E3.d1.p = c + 10 * Q + 4;   d.E3.d1.s = 1;
 }
 
 // single-thread setup of the extra constants; blob(n) (N, R1, ..., NINV) must already be set up.

@@ -48,14 +48,15 @@ template <int NTH>
 struct EncDigitBody {
   const uint32_t* consts; int const_quads;
   const uint32_t* prog; int nops, nodd; const uint32_t* m; const uint32_t* r; uint32_t* out; long batch; u4* tbl;
-  unsigned long long* counter;
-  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_encrypt_digit<NTH>(smem, id, prog, nops, nodd, m, r, out, batch, tbl, counter); }
+  unsigned long long* counter; const uint32_t* gzero;
+  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_encrypt_digit<NTH>(smem, id, prog, nops, nodd, m, r, out, batch, tbl, counter, gzero); }
 };
 template <int NTH, int W>
 struct PowDigitBody {
   const uint32_t* consts; int const_quads;
   const uint32_t* base; const uint32_t* exp; int exp_limbs; uint32_t* out; long batch; u4* tbl; unsigned long long* counter;
-  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_powmod_digit<NTH, W>(smem, id, base, exp, exp_limbs, out, batch, tbl, counter); }
+  const uint32_t* gzero;
+  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_powmod_digit<NTH, W>(smem, id, base, exp, exp_limbs, out, batch, tbl, counter, gzero); }
 };
 template <int NT>
 struct MulBody {
@@ -458,7 +459,7 @@ int do_encrypt_digit(pai_pub* k, const uint32_t* m_, const uint32_t* r, uint32_t
   unsigned long long* ctr = nullptr;
   rc = m->ctr.take(s, &ctr);
   if (rc) return rc;
-  B body{k->d_enc_consts, cq, k->d_prog, k->nops, k->nodd, m_, r, c, batch, (u4*)m->tbl.p, ctr};
+  B body{k->d_enc_consts, cq, k->d_prog, k->nops, k->nodd, m_, r, c, batch, (u4*)m->tbl.p, ctr, m->d_blob + dc_zero_offset(NTH)};
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
 }
 
@@ -475,7 +476,7 @@ int do_powmod_digit(pai_pub* k, const uint32_t* base, const uint32_t* d_exp, int
   unsigned long long* ctr = nullptr;
   rc = m->ctr.take(s, &ctr);
   if (rc) return rc;
-  B body{k->d_enc_consts, cq, base, d_exp, exp_limbs, out, batch, (u4*)m->tbl.p, ctr};
+  B body{k->d_enc_consts, cq, base, d_exp, exp_limbs, out, batch, (u4*)m->tbl.p, ctr, m->d_blob + dc_zero_offset(NTH)};
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
 }
 
@@ -743,10 +744,9 @@ int pai_pub_create(const uint32_t* n, int limbs, int device, pai_pub** out) {
     if (!rc) rc = rt_d2d(c, b, (size_t)h * 4, 0);                                  // N
     if (!rc) rc = rt_d2d(c + h, b + 4 * h, (size_t)(h + 8) * 4, 0);                // ONE | NINV
     if (!rc) rc = rt_d2d(c + 2 * h + 8, e, (size_t)3 * h * 4, 0);                  // KL | RR
-    if (!rc) rc = rt_d2d(c + 5 * h + 8, e + 5 * h, (size_t)h * 4, 0);              // ZERO
-    if (!rc) rc = rt_d2d(c + 6 * h + 8, e + 12 * h, (size_t)(2 * h + 8) * 4, 0);   // N2 | N3 | TOPS
-    if (!rc) rc = rt_d2d(c + 8 * h + 16, e + 3 * h, (size_t)2 * h * 4, 0);         // ONEM
-    if (!rc) rc = rt_d2d(c + 10 * h + 16, e + 6 * h, (size_t)2 * h * 4, 0);        // E3
+    if (!rc) rc = rt_d2d(c + 5 * h + 8, e + 12 * h, (size_t)(2 * h + 8) * 4, 0);   // N2 | N3 | TOPS
+    if (!rc) rc = rt_d2d(c + 7 * h + 16, e + 3 * h, (size_t)2 * h * 4, 0);         // ONEM
+    if (!rc) rc = rt_d2d(c + 9 * h + 16, e + 6 * h, (size_t)2 * h * 4, 0);         // E3
   }
   { const char* e = getenv("PAI_ENCRYPT_PATH"); k->use_digit = !(e && std::string(e) == "full"); }
   // exponent program for r^n: sliding windows of W_ENC bits over the public exponent n
