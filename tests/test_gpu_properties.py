@@ -192,3 +192,26 @@ def test_streams_and_cuda_graph(pkg, cuda_engine, gmp):
         graph.replay()
         torch.cuda.synchronize()
         assert bool((d_c == ref_c).all().item()) and bool((d_d == d_m).all().item())
+
+
+def test_all_kernel_paths_agree(pkg, cuda_engine, monkeypatch):
+    """The base-n digit kernels (default) and the full-width Montgomery kernels (PAI_*_PATH=full) must give
+    identical bits."""
+    n, p, q = _key(1024)
+    rng = random.Random(21)
+    m = [rng.randrange(n) for _ in range(300)] + [0, 1, n - 1]
+    r = [rng.randrange(1, n) for _ in m]
+    k = [rng.getrandbits(64) for _ in m[:150]] + [n - 1 - rng.getrandbits(40) for _ in m[150:]]
+    results = []
+    for env in ({}, {"PAI_ENCRYPT_PATH": "full", "PAI_DECRYPT_PATH": "full"}):
+        for key in ("PAI_ENCRYPT_PATH", "PAI_DECRYPT_PATH"):
+            monkeypatch.delenv(key, raising=False)
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        pub, priv = pkg.PublicContext(n), pkg.PrivateContext(p, q)       # the switches are read at context creation
+        c = pub.raw_encrypt(m, r)
+        t, st = pub.raw_mul(c, k)
+        results.append((c, priv.raw_decrypt(c), t, st, priv.raw_decrypt(t)))
+        pub.close(); priv.close()
+    assert results[0] == results[1]
+    assert results[0][1] == m
