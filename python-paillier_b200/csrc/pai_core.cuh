@@ -38,6 +38,14 @@ namespace pai {
 
 static const int TILE = 8;  // limbs per tile
 
+// CTA barrier used only to keep the warps of a CTA on the same ladder step (instruction-cache locality);
+// a no-op in the CPU simulation, where threads run one after the other.
+PAI_DEV void cta_step_sync() {
+#if !defined(PAI_HOSTSIM)
+  __syncthreads();
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // Operand descriptor: quad q (4 limbs) is at p[q * s].
 //   per-thread operand in the interleaved shared/global layout: p = base + tid, s = nthreads

@@ -119,9 +119,12 @@ PAI_DEV void cta_encrypt_digit(u4* smem, const CtaId& id, const uint32_t* prog, 
   cta_bufs<2 * NTH>(E.buf, 2, smem, dc_enc_limbs(NTH) / 4, id);
   E.tbl = cta_table_slots<2 * NTH>(tbl, id, nodd + 1);
   E.dc = &dc;
+  E.step_sync = 1;
   const int ln = 8 * NTH, lc = 16 * NTH;
-  RowSched sched = sched_init(id, counter, batch);
-  for (long g = sched_next_row(sched, id); g >= 0; g = sched_next_row(sched, id)) {
+  (void)counter;
+  // static chunks: every thread of the CTA runs the same number of identical ladders, so the per-step barrier is safe
+  for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
+    long g = chunk * id.nthr + id.tid;
     bool store = g < batch;
     if (!store) g = batch - 1;
     prog_encrypt_digit<NTH>(E, prog, nops, nodd, m + g * ln, r + g * ln, out + g * lc, store);
@@ -273,9 +276,11 @@ PAI_DEV void cta_decrypt_digit(u4* smem, const CtaId& id, int nwin_p, int nwin_q
   cta_bufs<2 * NTP>(E.buf, 2, smem, ddec_const_quads<NTP>(), id);
   E.tbl = cta_table_slots<2 * NTP>(tbl, id, 1 << W);
   E.dc = &P.dc;
+  E.step_sync = 1;
   const int lc = 32 * NTP, ln = 16 * NTP;
-  RowSched sched = sched_init(id, counter, batch);
-  for (long g = sched_next_row(sched, id); g >= 0; g = sched_next_row(sched, id)) {
+  (void)counter;
+  for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
+    long g = chunk * id.nthr + id.tid;
     bool store = g < batch;
     if (!store) g = batch - 1;
     prog_decrypt_digit<NTP, W>(E, P, Qs, pinvqM, c + g * lc, out + g * ln, store);
@@ -293,6 +298,7 @@ PAI_DEV void cta_powmod_digit(u4* smem, const CtaId& id, const uint32_t* base, c
   cta_bufs<2 * NTH>(E.buf, 2, smem, dc_pow_limbs(NTH) / 4, id);
   E.tbl = cta_table_slots<2 * NTH>(tbl, id, 1 << W);
   E.dc = &dc;
+  E.step_sync = 0;                  // per-element exponents: window counts differ between warps
   const int lc = 16 * NTH;
   RowSched sched = sched_init(id, counter, batch);
   for (long g = sched_next_row(sched, id); g >= 0; g = sched_next_row(sched, id)) {

@@ -468,6 +468,7 @@ struct DPowEnv {
   Opnd buf[2];
   Opnd tbl;           // entry e, quad q at tbl.p[(e * 4*NTH + q) * tbl.s]
   DigitEnv* dc;
+  int step_sync;      // 1: every thread of the CTA runs the same ladder -> barrier before each step (I-cache locality)
 };
 
 template <int NTH>
@@ -527,12 +528,14 @@ PAI_DEV int dpow_prog(const DPowEnv<NTH>& E, int bi, int sw, const uint32_t* pro
     const uint32_t op = prog[i];
     const int nsq = (int)(op >> 16), idx = (int)(op & 0xffffu);
     for (int s = 0; s < nsq; s++) {
+      if (E.step_sync) cta_step_sync();
       x = dview<NTH>(E.buf[cur], sw);
       dsqr<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, &dc);
       int t = cur; cur = oth; oth = t;
       sw = 1;
     }
     if (idx != 0xffff) {
+      if (E.step_sync) cta_step_sync();
       x = dview<NTH>(E.buf[cur], sw);
       const DNum te = dtbl_entry<NTH>(E, idx);
       dmul<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, te.d0, te.d1, &dc);
@@ -615,11 +618,13 @@ PAI_DEV int dpow_fixed(const DPowEnv<NTH>& E, int bi, int sw, const uint32_t* e,
   }
   for (int wi = nwin - 2; wi >= 0; wi--) {
     for (int s = 0; s < W; s++) {
+      if (E.step_sync) cta_step_sync();
       x = dview<NTH>(E.buf[cur], sw);
       dsqr<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, &dc);
       int t = cur; cur = oth; oth = t;
       sw = 1;
     }
+    if (E.step_sync) cta_step_sync();
     x = dview<NTH>(E.buf[cur], sw);
     const DNum te = dtbl_entry<NTH>(E, (int)exp_digit(e, nl, wi * W, W));
     dmul<NTH>(half_lo<NTH>(E.buf[oth]), half_hi<NTH>(E.buf[oth]), x.d0, x.d1, te.d0, te.d1, &dc);

@@ -652,12 +652,14 @@ int pai_device_count(void) { return rt_device_count(); }
 long pai_launch_count(void) { return g_launches.load(); }
 
 int pai_mod_create(const uint32_t* modulus, int limbs, int device, pai_mod** out) {
+  DeviceGuard device_guard_; (void)device_guard_;
   return mod_create_impl(modulus, limbs, device, 0, 0, out);
 }
 int pai_mod_destroy(pai_mod* m) { mod_free(m); return 0; }
 int pai_mod_limbs(const pai_mod* m) { return m ? m->L : PAI_E_ARG; }
 
 int pai_mod_mulmod(pai_mod* m, const uint32_t* d_a, const uint32_t* d_b, uint32_t* d_out, long batch, void* stream) {
+  DeviceGuard device_guard_; (void)device_guard_;
   if (!m || !d_a || !d_b || !d_out || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
   if (batch == 0) return 0;
   int rc = rt_set_device(m->device);
@@ -676,6 +678,7 @@ static int powmod_common(pai_mod* m, const uint32_t* d_base, int base_limbs, con
 
 int pai_mod_powmod_shared(pai_mod* m, const uint32_t* d_base, int base_limbs, const uint32_t* exponent, int exp_limbs,
                           uint32_t* d_out, long batch, void* stream) {
+  DeviceGuard device_guard_; (void)device_guard_;
   if (!m || !d_base || !exponent || !d_out || batch < 0 || exp_limbs <= 0) { g_err = "bad argument"; return PAI_E_ARG; }
   if (batch == 0) return 0;
   int rc = rt_set_device(m->device);
@@ -691,6 +694,7 @@ int pai_mod_powmod_shared(pai_mod* m, const uint32_t* d_base, int base_limbs, co
 
 int pai_mod_powmod(pai_mod* m, const uint32_t* d_base, int base_limbs, const uint32_t* d_exp, int exp_limbs,
                    uint32_t* d_out, long batch, void* stream) {
+  DeviceGuard device_guard_; (void)device_guard_;
   if (!m || !d_base || !d_exp || !d_out || batch < 0 || exp_limbs <= 0) { g_err = "bad argument"; return PAI_E_ARG; }
   if (batch == 0) return 0;
   int rc = rt_set_device(m->device);
@@ -699,6 +703,7 @@ int pai_mod_powmod(pai_mod* m, const uint32_t* d_base, int base_limbs, const uin
 }
 
 int pai_mod_invert(pai_mod* m, const uint32_t* d_a, int a_limbs, uint32_t* d_out, int32_t* d_status, long batch, void* stream) {
+  DeviceGuard device_guard_; (void)device_guard_;
   if (!m || !d_a || !d_out || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
   if (a_limbs != m->L) { g_err = "a_limbs must equal pai_mod_limbs()"; return PAI_E_ARG; }
   if (batch == 0) return 0;
@@ -710,6 +715,7 @@ int pai_mod_invert(pai_mod* m, const uint32_t* d_a, int a_limbs, uint32_t* d_out
 
 // ---------------------------------------------------------------------------------------- public key
 int pai_pub_create(const uint32_t* n, int limbs, int device, pai_pub** out) {
+  DeviceGuard device_guard_; (void)device_guard_;
   if (!n || !out || limbs <= 0) { g_err = "bad argument"; return PAI_E_ARG; }
   int eff = eff_limbs(n, limbs);
   if (eff == 0 || !(n[0] & 1u)) { g_err = "n must be odd"; return PAI_E_ARG; }
@@ -776,6 +782,7 @@ int pai_pub_n_limbs(const pai_pub* k) { return k ? k->ln : PAI_E_ARG; }
 int pai_pub_c_limbs(const pai_pub* k) { return k ? 2 * k->ln : PAI_E_ARG; }
 
 int pai_encrypt(pai_pub* k, const uint32_t* d_m, const uint32_t* d_r, uint32_t* d_c, long batch, void* stream) {
+  DeviceGuard device_guard_; (void)device_guard_;
   if (!k || !d_m || !d_r || !d_c || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
   if (batch == 0) return 0;
   int rc = rt_set_device(k->nsq->device);
@@ -785,10 +792,12 @@ int pai_encrypt(pai_pub* k, const uint32_t* d_m, const uint32_t* d_r, uint32_t* 
   return rc;
 }
 int pai_raw_add(pai_pub* k, const uint32_t* d_a, const uint32_t* d_b, uint32_t* d_c, long batch, void* stream) {
+  DeviceGuard device_guard_; (void)device_guard_;
   if (!k) { g_err = "bad argument"; return PAI_E_ARG; }
   return pai_mod_mulmod(k->nsq, d_a, d_b, d_c, batch, stream);
 }
 int pai_raw_mul(pai_pub* k, const uint32_t* d_a, const uint32_t* d_s, uint32_t* d_c, int32_t* d_status, long batch, void* stream) {
+  DeviceGuard device_guard_; (void)device_guard_;
   if (!k || !d_a || !d_s || !d_c || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
   if (batch == 0) return 0;
   pai_mod* m = k->nsq;
@@ -821,6 +830,7 @@ int pai_raw_mul(pai_pub* k, const uint32_t* d_a, const uint32_t* d_s, uint32_t* 
 
 // ---------------------------------------------------------------------------------------- private key
 int pai_priv_create(const uint32_t* p, const uint32_t* q, int limbs, int device, pai_priv** out) {
+  DeviceGuard device_guard_; (void)device_guard_;
   if (!p || !q || !out || limbs <= 0) { g_err = "bad argument"; return PAI_E_ARG; }
   int ep = eff_limbs(p, limbs), eq = eff_limbs(q, limbs);
   if (!ep || !eq || !(p[0] & 1u) || !(q[0] & 1u)) { g_err = "p and q must be odd"; return PAI_E_ARG; }
@@ -883,6 +893,7 @@ int pai_priv_get(const pai_priv* k, uint32_t* p, uint32_t* q, uint32_t* p_invers
   return 0;
 }
 int pai_decrypt(pai_priv* k, const uint32_t* d_c, uint32_t* d_m, long batch, void* stream) {
+  DeviceGuard device_guard_; (void)device_guard_;
   if (!k || !d_c || !d_m || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
   if (batch == 0) return 0;
   int rc = rt_set_device(k->device);
@@ -896,6 +907,7 @@ int pai_decrypt(pai_priv* k, const uint32_t* d_c, uint32_t* d_m, long batch, voi
 #define STAGE_IN(buf, host, bytes) do { rc = (buf).ensure(bytes); if (!rc) rc = rt_h2d((buf).p, host, bytes, 0); if (rc) return rc; } while (0)
 
 int pai_encrypt_host(pai_pub* k, const uint32_t* m, const uint32_t* r, uint32_t* c, long batch) {
+  DeviceGuard device_guard_; (void)device_guard_;
   if (!k || !m || !r || !c || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
   if (batch == 0) return 0;
   int rc = rt_set_device(k->nsq->device);
@@ -910,6 +922,7 @@ int pai_encrypt_host(pai_pub* k, const uint32_t* m, const uint32_t* r, uint32_t*
   return rc;
 }
 int pai_raw_add_host(pai_pub* k, const uint32_t* a, const uint32_t* b, uint32_t* c, long batch) {
+  DeviceGuard device_guard_; (void)device_guard_;
   if (!k || !a || !b || !c || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
   if (batch == 0) return 0;
   int rc = rt_set_device(k->nsq->device);
@@ -924,6 +937,7 @@ int pai_raw_add_host(pai_pub* k, const uint32_t* a, const uint32_t* b, uint32_t*
   return rc;
 }
 int pai_raw_mul_host(pai_pub* k, const uint32_t* a, const uint32_t* s, uint32_t* c, int32_t* status, long batch) {
+  DeviceGuard device_guard_; (void)device_guard_;
   if (!k || !a || !s || !c || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
   if (batch == 0) return 0;
   int rc = rt_set_device(k->nsq->device);
@@ -940,6 +954,7 @@ int pai_raw_mul_host(pai_pub* k, const uint32_t* a, const uint32_t* s, uint32_t*
   return rc;
 }
 int pai_decrypt_host(pai_priv* k, const uint32_t* c, uint32_t* m, long batch) {
+  DeviceGuard device_guard_; (void)device_guard_;
   if (!k || !c || !m || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
   if (batch == 0) return 0;
   int rc = rt_set_device(k->device);
@@ -953,6 +968,7 @@ int pai_decrypt_host(pai_priv* k, const uint32_t* c, uint32_t* m, long batch) {
   return rc;
 }
 int pai_mod_mulmod_host(pai_mod* m, const uint32_t* a, const uint32_t* b, uint32_t* out, long batch) {
+  DeviceGuard device_guard_; (void)device_guard_;
   if (!m || !a || !b || !out || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
   if (batch == 0) return 0;
   int rc = rt_set_device(m->device);
@@ -968,6 +984,7 @@ int pai_mod_mulmod_host(pai_mod* m, const uint32_t* a, const uint32_t* b, uint32
 }
 int pai_mod_powmod_host(pai_mod* m, const uint32_t* base, int base_limbs, const uint32_t* exp, int exp_limbs, int shared_exp,
                         uint32_t* out, long batch) {
+  DeviceGuard device_guard_; (void)device_guard_;
   if (!m || !base || !exp || !out || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
   if (batch == 0) return 0;
   int rc = rt_set_device(m->device);
@@ -986,6 +1003,7 @@ int pai_mod_powmod_host(pai_mod* m, const uint32_t* base, int base_limbs, const 
   return rc;
 }
 int pai_mod_invert_host(pai_mod* m, const uint32_t* a, int a_limbs, uint32_t* out, int32_t* status, long batch) {
+  DeviceGuard device_guard_; (void)device_guard_;
   if (!m || !a || !out || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
   if (batch == 0) return 0;
   int rc = rt_set_device(m->device);

@@ -45,6 +45,13 @@ static inline int rt_device_count() {
   return n;
 }
 static inline int rt_set_device(int dev) { RT_CHECK(cudaSetDevice(dev)); return 0; }
+// restores the caller's current device when an entry point returns (contexts pin their own device; a host
+// program that also uses torch or other CUDA libraries must not see its current device change under it)
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 static inline int rt_malloc(void** p, size_t bytes) { RT_CHECK(cudaMalloc(p, bytes ? bytes : 16)); return 0; }
 static inline void rt_free(void* p) { if (p) cudaFree(p); }
 static inline int rt_h2d(void* d, const void* h, size_t n, rt_stream s) { RT_CHECK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); return 0; }
@@ -87,6 +94,7 @@ typedef void* rt_stream;
 #define RT_CHECK(expr) do { if ((expr) != 0) return PAI_E_CUDA; } while (0)
 static inline int rt_device_count() { return 1; }
 static inline int rt_set_device(int) { return 0; }
+struct DeviceGuard {};
 static inline int rt_malloc(void** p, size_t bytes) { *p = aligned_alloc(64, ((bytes ? bytes : 16) + 63) / 64 * 64); return *p ? 0 : -2; }
 static inline void rt_free(void* p) { free(p); }
 static inline int rt_h2d(void* d, const void* h, size_t n, rt_stream) { memcpy(d, h, n); return 0; }
