@@ -288,7 +288,9 @@ PAI_DEV void cta_decrypt_digit(u4* smem, const CtaId& id, int nwin_p, int nwin_q
 }
 
 
-// ---- c^k mod n^2 in digit form (raw_mul).  consts = compact constants with ONEM and E3 (dc_pow_limbs)
+// ---- c^k mod n^2 in digit form (raw_mul).  consts = compact constants with ONEM and E3 (dc_pow_limbs).
+// Exponents differ per element; the window count is made CTA-uniform (max over the CTA through one shared word)
+// so that the per-step barrier of the ladder is safe here too.
 template <int NTH, int W>
 PAI_DEV void cta_powmod_digit(u4* smem, const CtaId& id, const uint32_t* base, const uint32_t* exp, int exp_limbs, uint32_t* out,
                               long batch, u4* tbl, unsigned long long* counter, const uint32_t* gzero) {
@@ -298,16 +300,25 @@ PAI_DEV void cta_powmod_digit(u4* smem, const CtaId& id, const uint32_t* base, c
   cta_bufs<2 * NTH>(E.buf, 2, smem, dc_pow_limbs(NTH) / 4, id);
   E.tbl = cta_table_slots<2 * NTH>(tbl, id, 1 << W);
   E.dc = &dc;
-  E.step_sync = 0;                  // per-element exponents: window counts differ between warps
+  E.step_sync = 1;
   const int lc = 16 * NTH;
-  RowSched sched = sched_init(id, counter, batch);
-  for (long g = sched_next_row(sched, id); g >= 0; g = sched_next_row(sched, id)) {
+  (void)counter;
+#if !defined(PAI_HOSTSIM)
+  __shared__ int s_nwin;
+#endif
+  for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
+    long g = chunk * id.nthr + id.tid;
     bool store = g < batch;
     if (!store) g = batch - 1;
     const uint32_t* e = exp + g * exp_limbs;
     int nwin = (limbs_bitlen(e, exp_limbs) + W - 1) / W;
 #if !defined(PAI_HOSTSIM)
+    if (id.tid == 0) s_nwin = 0;
+    __syncthreads();
     nwin = __reduce_max_sync(0xffffffffu, nwin);
+    if ((id.tid & 31) == 0) atomicMax(&s_nwin, nwin);
+    __syncthreads();
+    nwin = s_nwin;
 #endif
     prog_powmod_digit<NTH, W>(E, base + g * lc, e, exp_limbs, nwin, out + g * lc, store);
   }
