@@ -94,7 +94,7 @@ PAI_DEV void cta_encrypt(u4* smem, const CtaId& id, const uint32_t* prog, int no
   ModC mc;
   modc_bind(mc, smem, NT);
   PowEnv<NT> E;
-  cta_bufs<NT>(E.buf, 2, smem, enc_const_quads<NT>(), id);       // two operand buffers (mont_pow2)
+  cta_bufs<NT>(E.buf, 2, smem, enc_const_quads<NT>(), id);       // two operand buffers (mont_pow_prog)
   E.tbl = cta_table_slots<NT>(tbl, id, nodd + 1);
   E.mc = &mc;
   Opnd nbc{smem + mc_limbs(NT) / 4, 1};

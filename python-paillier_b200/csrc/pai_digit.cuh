@@ -47,15 +47,6 @@ struct DigitEnv {
   DNum RR, ONEM, E3, E4, E5;
 };
 
-// (legacy descriptor, kept for documentation of the constants)
-struct DigitC {
-  Opnd N, NI;      // n, tile holding -n^-1 mod 2^256
-  Opnd KL;         // n - (R mod n):  K = R + KL is the multiple of n used to keep phase 2 non-negative
-  DNum RR;         // digits of R^2 mod n^2  (to enter the Montgomery domain)
-  DNum ONEM;       // digits of R   mod n^2  (Montgomery form of 1)
-  DNum ONE;        // (1, 0)
-};
-
 // x = K - x (NT tiles); returns the borrow (1 if x > K)
 template <int NT>
 PAI_DEV uint32_t big_rsub(const Opnd& x, const Opnd& K) {
@@ -69,20 +60,6 @@ PAI_DEV uint32_t big_rsub(const Opnd& x, const Opnd& K) {
   return bo;
 }
 
-// value = x + ovf * 2^(256 NT), value < (ROUNDS+... ) * N : subtract N up to ROUNDS times -> canonical
-template <int NT, int ROUNDS>
-PAI_DEV void big_reduce_small(const Opnd& x, const Opnd& N, uint32_t ovf) {
-  for (int r = 0; r < ROUNDS; r++) {
-    uint32_t bo = big_sub_borrow<NT>(x, N);                 // 1 iff x < N as NT-tile numbers
-    uint32_t need = (ovf != 0u) | (bo ^ 1u);
-    big_sub_masked<NT>(x, x, N, 0u - need);
-    ovf -= need & bo;                                       // the subtraction borrowed from the overflow word
-  }
-}
-
-// Z = X * Y * R^-1 mod n^2 in digit form.  Output: Z0 in ohi, Z1 in olo (the two halves of one buffer, or any
-// two disjoint NTH-tile regions that alias none of the inputs).  X0 may be any value < R if Y0 < n (and
-// vice versa); X1, Y1 may be any values < R.
 // Reduction of the second phase: V = olo + ovf*R < 3n + 2.  b1, b2, b3 are the borrows of olo - (c*n mod R)
 // gathered while the result tiles were produced; q = #{c : V >= c*n}; one masked subtraction of q*n.
 template <int NTH>

@@ -126,10 +126,9 @@ PAI_DEV int mont_pow(const PowEnv<NT>& E, int bi, const uint32_t* e, int nl, int
   return cur;
 }
 
-// Two-buffer variant: table entries are consumed straight from the global table as the `b` operand of
+// Two-buffer exponentiation: table entries are consumed straight from the global table as the `b` operand of
 // mont_mul (never staged in shared memory), so a thread needs 2 x 32*NT bytes of shared memory instead
 // of 3 x -- at 4096-bit moduli that is 224 instead of 128 resident threads per SM.
-//   base (Montgomery form) in buf[bi] (bi in {0,1}); returns the buffer index of the result.
 template <int NT>
 PAI_DEV Opnd tbl_entry(const PowEnv<NT>& E, int e) {
   Opnd o;
@@ -138,44 +137,11 @@ PAI_DEV Opnd tbl_entry(const PowEnv<NT>& E, int e) {
   return o;
 }
 
-template <int NT, int W, bool SKIPZERO>
-PAI_DEV int mont_pow2(const PowEnv<NT>& E, int bi, const uint32_t* e, int nl, int nwin) {
-  const ModC& mc = *E.mc;
-  int cur = bi, oth = bi ^ 1;
-  if (nwin <= 0) {
-    big_copy<NT>(E.buf[oth], mc.R1);
-    return oth;
-  }
-  tbl_store<NT>(E, 0, mc.R1);
-  tbl_store<NT>(E, 1, E.buf[bi]);
-  const Opnd t1 = tbl_entry<NT>(E, 1);
-  mont_sqr<NT>(E.buf[oth], E.buf[cur], mc.N, mc.ninv);
-  { int t = cur; cur = oth; oth = t; }
-  tbl_store<NT>(E, 2, E.buf[cur]);
-  for (int i = 3; i < (1 << W); i++) {
-    mont_mul<NT>(E.buf[oth], E.buf[cur], t1, mc.N, mc.ninv);
-    { int t = cur; cur = oth; oth = t; }
-    tbl_store<NT>(E, i, E.buf[cur]);
-  }
-  tbl_load<NT>(E, (int)exp_digit(e, nl, (nwin - 1) * W, W), E.buf[cur]);
-  for (int wi = nwin - 2; wi >= 0; wi--) {
-    for (int s = 0; s < W; s++) {
-      mont_sqr<NT>(E.buf[oth], E.buf[cur], mc.N, mc.ninv);
-      int t = cur; cur = oth; oth = t;
-    }
-    int d = (int)exp_digit(e, nl, wi * W, W);
-    if (SKIPZERO && d == 0) continue;
-    mont_mul<NT>(E.buf[oth], E.buf[cur], tbl_entry<NT>(E, d), mc.N, mc.ninv);
-    int t = cur; cur = oth; oth = t;
-  }
-  return cur;
-}
-
 // Sliding-window exponentiation driven by a host-built "exponent program" (public exponent shared by
 // the whole batch: encrypt's n).  prog[i] = (nsq << 16) | idx : square nsq times, then multiply by the
 // odd power T[idx] = base^(2 idx + 1)  (idx = 0xffff: no multiplication).  prog[0] only selects the
 // initial value T[idx].  Table slots: T[0 .. 2^(w-1)) odd powers, slot 2^(w-1) = base^2 (build helper).
-// Two shared-memory buffers, table entries consumed from global memory like mont_pow2.
+// Two shared-memory buffers, table entries consumed straight from global memory.
 template <int NT>
 PAI_DEV int mont_pow_prog(const PowEnv<NT>& E, int bi, const uint32_t* prog, int nops, int nodd) {
   const ModC& mc = *E.mc;
@@ -211,7 +177,13 @@ PAI_DEV int mont_pow_prog(const PowEnv<NT>& E, int bi, const uint32_t* prog, int
   return cur;
 }
 
-// raw_encrypt with two shared-memory buffers (see prog_encrypt below for the semantics)
+// raw_encrypt:  c = (1 + n*m) * r^n mod n^2          (phe/paillier.py:102-139)
+// Both reference branches for the nude ciphertext (:125-134) equal n*(m mod n)+1 mod n^2
+// (because (1+n*a)^-1 = 1-n*a mod n^2), and the final Montgomery multiplication reduces any
+// m, r < 2^(32*Ln) for free, so no inversion and no range split is needed here.
+//   NT  = tiles of n^2 (even); n, m, r have NT/2 tiles.  mc = constants of n^2.
+//   nbc = n as a broadcast operand (NT/2 tiles); e = limbs of n (the exponent), nwin windows.
+// (full-width Montgomery variant with two shared-memory buffers; the default path is prog_encrypt_digit)
 template <int NT>
 PAI_DEV void prog_encrypt2(const PowEnv<NT>& E, const Opnd& nbc, const uint32_t* prog, int nops, int nodd,
                            const uint32_t* m_row, const uint32_t* r_row, uint32_t* out_row, bool store) {
@@ -224,28 +196,6 @@ PAI_DEV void prog_encrypt2(const PowEnv<NT>& E, const Opnd& nbc, const uint32_t*
   load_row(E.buf[a], m_row, NT, NT);
   big_mul<NT / 2, NT / 2, NT>(E.buf[b], E.buf[a], nbc, 1u);               // n*m + 1
   mont_mul<NT>(E.buf[a], E.buf[b], tbl_entry<NT>(E, 0), mc.N, mc.ninv);   // (n*m+1) * r^n mod n^2
-  if (store) store_row(out_row, E.buf[a], 2 * NT);
-}
-
-// ------------------------------------------------------------------------------------------------
-// raw_encrypt:  c = (1 + n*m) * r^n mod n^2          (phe/paillier.py:102-139)
-// Both reference branches for the nude ciphertext (:125-134) equal n*(m mod n)+1 mod n^2
-// (because (1+n*a)^-1 = 1-n*a mod n^2), and the final Montgomery multiplication reduces any
-// m, r < 2^(32*Ln) for free, so no inversion and no range split is needed here.
-//   NT  = tiles of n^2 (even); n, m, r have NT/2 tiles.  mc = constants of n^2.
-//   nbc = n as a broadcast operand (NT/2 tiles); e = limbs of n (the exponent), nwin windows.
-template <int NT, int W>
-PAI_DEV void prog_encrypt(const PowEnv<NT>& E, const Opnd& nbc, const uint32_t* e, int nl, int nwin,
-                          const uint32_t* m_row, const uint32_t* r_row, uint32_t* out_row, bool store) {
-  const ModC& mc = *E.mc;
-  load_row(E.buf[0], r_row, NT, 2 * NT);
-  mont_mul<NT>(E.buf[1], E.buf[0], mc.R2, mc.N, mc.ninv);                 // r*R mod n^2
-  int cur = mont_pow<NT, W, true>(E, 1, e, nl, nwin);                     // (r^n)*R mod n^2
-  int a = cur == 2 ? 0 : cur + 1;
-  int b = a == 2 ? 0 : a + 1;
-  load_row(E.buf[a], m_row, NT, NT);
-  big_mul<NT / 2, NT / 2, NT>(E.buf[b], E.buf[a], nbc, 1u);               // n*m + 1  (< 2^(32 L))
-  mont_mul<NT>(E.buf[a], E.buf[cur], E.buf[b], mc.N, mc.ninv);            // r^n * (n*m+1) mod n^2
   if (store) store_row(out_row, E.buf[a], 2 * NT);
 }
 
