@@ -74,6 +74,10 @@ int pai_pub_c_limbs(const pai_pub* k);     /* 2*Ln: limbs of ciphertexts        
 /* c[i] = (1 + n*m[i]) * r[i]^n mod n^2        raw_encrypt, phe/paillier.py:102-139
  * (= obfuscate of the nude ciphertext, :603-624).  Any m, r < 2^(32 Ln) is accepted and reduced. */
 int pai_encrypt(pai_pub* k, const uint32_t* d_m, const uint32_t* d_r, uint32_t* d_c, long batch, void* stream);
+/* r[i] uniform in [1, n), the batched form of get_random_lt_n (phe/paillier.py:141-143): ChaCha20 keystream of
+ * the 32-byte seed (take it from the OS CSPRNG) and the 64-bit nonce (distinct per call), rejection sampled on the
+ * device.  d_r: [batch][pai_pub_n_limbs()]. */
+int pai_random_lt_n(pai_pub* k, const uint8_t* seed32, unsigned long long nonce, uint32_t* d_r, long batch, void* stream);
 /* c[i] = a[i] * b[i] mod n^2                  _raw_add, phe/paillier.py:705-719 */
 int pai_raw_add(pai_pub* k, const uint32_t* d_a, const uint32_t* d_b, uint32_t* d_c, long batch, void* stream);
 /* c[i] = a[i] ^ s[i] mod n^2 for 0 <= s[i] < n, with the reference's negative-scalar branch

@@ -9,6 +9,7 @@
 #pragma once
 #include "pai_kernels.cuh"
 #include "pai_digit.cuh"
+#include "pai_rng.cuh"
 
 namespace pai {
 

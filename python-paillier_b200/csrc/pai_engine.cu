@@ -79,6 +79,14 @@ struct InvBody {
   const uint32_t* a; int a_tiles; const int32_t* flags; uint32_t* out; int32_t* status; long batch;
   PAI_MEM void run(u4* smem, const CtaId& id) const { cta_invert<NT>(smem, id, a, a_tiles, flags, out, status, batch); }
 };
+struct RngBody {
+  const uint32_t* consts; int const_quads;
+  uint32_t key[8]; unsigned long long nonce; const uint32_t* n; int ln, nbits; uint32_t* out; long batch;
+  PAI_MEM void run(u4*, const CtaId& id) const {
+    for (long g = (long)id.cta * id.nthr + id.tid; g < batch; g += (long)id.ncta * id.nthr)
+      rng_fill_lt_n(key, nonce, (uint64_t)g, n, ln, nbits, out + g * ln);
+  }
+};
 struct PrepBody {
   const uint32_t* consts; int const_quads;
   const uint32_t* n; const uint32_t* thresh; int ln; const uint32_t* s; uint32_t* e_out; int32_t* flag; long batch;
@@ -790,6 +798,19 @@ int pai_encrypt(pai_pub* k, const uint32_t* d_m, const uint32_t* d_r, uint32_t* 
   if (k->use_digit) { DISPATCH_NTH(k->nmod->NT, rc = do_encrypt_digit<NTH>(k, d_m, d_r, d_c, batch, (rt_stream)stream)); }
   else { DISPATCH_NT(k->nsq->NT, rc = do_encrypt<NT>(k, d_m, d_r, d_c, batch, (rt_stream)stream)); }
   return rc;
+}
+int pai_random_lt_n(pai_pub* k, const uint8_t* seed32, unsigned long long nonce, uint32_t* d_r, long batch, void* stream) {
+  DeviceGuard device_guard_; (void)device_guard_;
+  if (!k || !seed32 || !d_r || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  if (batch == 0) return 0;
+  int rc = rt_set_device(k->nsq->device);
+  if (rc) return rc;
+  RngBody b;
+  b.consts = nullptr; b.const_quads = 0;
+  memcpy(b.key, seed32, 32);
+  b.nonce = nonce; b.n = k->d_nth; b.ln = k->ln; b.nbits = bit_length(k->h_n); b.out = d_r; b.batch = batch;
+  long blocks = (batch + 127) / 128;
+  return rt_launch(b, (int)std::min(blocks, (long)rt_sm_count(k->nsq->device) * 16), 128, 0, (rt_stream)stream);
 }
 int pai_raw_add(pai_pub* k, const uint32_t* d_a, const uint32_t* d_b, uint32_t* d_c, long batch, void* stream) {
   DeviceGuard device_guard_; (void)device_guard_;

@@ -52,6 +52,7 @@ SYMBOLS = {
     "pai_pub_n_limbs": (ctypes.c_int, [_vp]),
     "pai_pub_c_limbs": (ctypes.c_int, [_vp]),
     "pai_encrypt": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_long, _vp]),
+    "pai_random_lt_n": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_ulonglong, _vp, ctypes.c_long, _vp]),
     "pai_raw_add": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_long, _vp]),
     "pai_raw_mul": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_long, _vp]),
     "pai_priv_create": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
@@ -280,6 +281,14 @@ class PublicContext:
     # ---- device-pointer API (torch tensors / raw addresses), asynchronous on `stream`
     def encrypt_dev(self, d_m, d_r, d_c, batch, stream=None):
         self.eng.check(self.eng.lib.pai_encrypt(self.h, _ptr(d_m), _ptr(d_r), _ptr(d_c), batch, _ptr(stream)))
+
+    def random_lt_n_dev(self, d_r, batch, seed=None, nonce=0, stream=None):
+        """Fill d_r [batch, n_limbs] with r uniform in [1, n) on the device (ChaCha20 of a 32-byte seed; default:
+        a fresh seed from os.urandom) -- the batched get_random_lt_n (phe/paillier.py:141-143)."""
+        seed = os.urandom(32) if seed is None else bytes(seed)
+        if len(seed) != 32:
+            raise ValueError("seed must be 32 bytes")
+        self.eng.check(self.eng.lib.pai_random_lt_n(self.h, seed, nonce, _ptr(d_r), batch, _ptr(stream)))
 
     def raw_add_dev(self, d_a, d_b, d_c, batch, stream=None):
         self.eng.check(self.eng.lib.pai_raw_add(self.h, _ptr(d_a), _ptr(d_b), _ptr(d_c), batch, _ptr(stream)))

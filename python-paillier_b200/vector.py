@@ -178,11 +178,15 @@ class EncryptedVector(object):
         ctx = public_key.engine_context()
         count = int(m_limbs.shape[0])
         obf = r_values is None
-        if r_values is None:
-            r_values = random_r_values(public_key.n, count)
         torch = _torch()
         d_m = _to_dev(m_limbs, ctx)
-        d_r = _to_dev(ints_to_limbs(list(r_values), ctx.n_limbs), ctx)
+        if r_values is None:
+            # fresh obfuscators drawn on the device from a ChaCha20 stream keyed by os.urandom (pai_rng.cuh)
+            d_r = torch.empty((count, ctx.n_limbs), dtype=torch.int32, device=d_m.device)
+            if count:
+                ctx.random_lt_n_dev(d_r, count)
+        else:
+            d_r = _to_dev(ints_to_limbs(list(r_values), ctx.n_limbs), ctx)
         d_c = torch.empty((count, ctx.c_limbs), dtype=torch.int32, device=d_m.device)
         if count:
             ctx.encrypt_dev(d_m, d_r, d_c, count)
@@ -224,7 +228,8 @@ class EncryptedVector(object):
         count = len(self)
         if count:
             torch = _torch()
-            d_r = _to_dev(ints_to_limbs(random_r_values(self.public_key.n, count), ctx.n_limbs), ctx)
+            d_r = torch.empty((count, ctx.n_limbs), dtype=torch.int32, device=self.limbs.device)
+            ctx.random_lt_n_dev(d_r, count)
             d_zero = torch.zeros((count, ctx.n_limbs), dtype=torch.int32, device=self.limbs.device)
             d_rn = torch.empty_like(self.limbs)
             ctx.encrypt_dev(d_zero, d_r, d_rn, count)
@@ -257,12 +262,23 @@ class EncryptedVector(object):
         limbs = self.limbs
         if len(idx):
             torch = _torch()
+            ctx = self.public_key.engine_context()
             tidx = torch.from_numpy(idx).to(limbs.device)
-            factors = [pow(EncodedNumber.BASE, int(d)) for d in (self.exponents[idx] - new_exps[idx])]
-            encs = [EncodedNumber.encode(self.public_key, f).encoding for f in factors]
-            sub = self._raw_mul_rows(limbs[tidx].contiguous(), encs)
+            # the scalar BASE**delta is a small positive int: its encoding is the integer itself (exponent 0), so the
+            # scalar limb matrix is built per distinct delta without touching EncodedNumber for every element
+            deltas = (self.exponents[idx] - new_exps[idx]).astype(np.int64)
+            scal = np.zeros((len(idx), ctx.n_limbs), dtype=np.uint32)
+            for d in np.unique(deltas):
+                factor = pow(EncodedNumber.BASE, int(d))
+                if factor > self.public_key.max_int:
+                    raise ValueError('Integer needs to be within +/- %d but got %d' % (self.public_key.max_int, factor))
+                scal[deltas == d] = ints_to_limbs([factor], ctx.n_limbs)[0]
+            sub = limbs[tidx].contiguous()
+            out = torch.empty_like(sub)
+            status = torch.zeros((len(idx),), dtype=torch.int32, device=limbs.device)
+            ctx.raw_mul_dev(sub, _to_dev(scal, ctx), out, status, len(idx))
             limbs = limbs.clone()
-            limbs[tidx] = sub
+            limbs[tidx] = out
         return EncryptedVector(self.public_key, limbs, new_exps.copy(), obfuscated=self._obfuscated and not len(idx))
 
     def __add__(self, other):

@@ -215,3 +215,38 @@ def test_all_kernel_paths_agree(pkg, cuda_engine, monkeypatch):
         pub.close(); priv.close()
     assert results[0] == results[1]
     assert results[0][1] == m
+
+
+def test_device_obfuscators(pkg, cuda_engine):
+    """pai_random_lt_n on the GPU: same stream as the simulation build for a seed (the keystream itself is pinned to
+    an independent ChaCha20 in tests/test_rng_hostsim.py), 1 <= r < n, distinct rows, fresh per call by default."""
+    import torch
+    import __graft_entry__ as ge
+    n, p, q = _key(2048)
+    pub = pkg.PublicContext(n)
+    batch = 50000
+    d_r = torch.empty((batch, pub.n_limbs), dtype=torch.int32, device="cuda")
+    seed = bytes(range(32))
+    pub.random_lt_n_dev(d_r, batch, seed=seed, nonce=7)
+    torch.cuda.synchronize()
+    r = d_r.cpu().numpy().view(np.uint32)
+    sim = pkg.Engine(ge.build_hostsim())
+    spub = pkg.PublicContext(n, engine=sim)
+    ref = np.zeros((64, spub.n_limbs), dtype=np.uint32)
+    spub.random_lt_n_dev(ref, 64, seed=seed, nonce=7)
+    assert (r[:64] == ref).all()
+    vals = pkg.limbs_to_ints(r[:2000])
+    assert all(1 <= v < n for v in vals)
+    assert len(np.unique(r[:, :4].copy().view([("", np.uint32)] * 4))) == batch
+    d_r2 = torch.empty_like(d_r)
+    pub.random_lt_n_dev(d_r2, batch)
+    assert not bool((d_r2 == d_r).all(dim=1).any().item())
+    # and an encrypt/decrypt round trip with device-drawn r
+    priv = pkg.PrivateContext(p, q)
+    m = _rand_rows(np.random.default_rng(1), batch, pub.n_limbs, 63)
+    d_m = torch.from_numpy(m.view(np.int32)).cuda()
+    d_c = torch.empty((batch, pub.c_limbs), dtype=torch.int32, device="cuda")
+    d_d = torch.empty_like(d_m)
+    pub.encrypt_dev(d_m, d_r2, d_c, batch)
+    priv.decrypt_dev(d_c, d_d, batch)
+    assert bool((d_d == d_m).all().item())
