@@ -98,6 +98,16 @@ int pai_priv_get(const pai_priv* k, uint32_t* p, uint32_t* q, uint32_t* p_invers
 /* m[i] = raw_decrypt(c[i]) with CRT             phe/paillier.py:328-374 */
 int pai_decrypt(pai_priv* k, const uint32_t* d_c, uint32_t* d_m, long batch, void* stream);
 
+/* ---- decimal wire format: the radix conversion behind the reference's JSON serialisation ---------
+ * (docs/serialisation.rst:24-42 ships ciphertexts as str(int); phe/command_line.py:120-131, 267-276 likewise.)
+ * Text rows are fixed-width fields of pai_decimal_width(limbs) ASCII digits, right aligned, '0' padded, row-major
+ * [batch][width], device memory.  pai_decimal_to_limbs accepts any width; d_status[i] (may be NULL) = 1 where a row
+ * holds a character that is not a digit, 2 where the value needs more than `limbs` limbs (the row is zeroed). */
+int pai_decimal_width(int limbs);
+int pai_limbs_to_decimal(const uint32_t* d_limbs, int limbs, uint8_t* d_text, long batch, int device, void* stream);
+int pai_decimal_to_limbs(const uint8_t* d_text, int width, uint32_t* d_limbs, int limbs, int32_t* d_status, long batch, int device,
+                         void* stream);
+
 /* ---- host-pointer convenience variants (H2D + kernel + D2H inside; synchronous) ---------------- */
 int pai_encrypt_host(pai_pub* k, const uint32_t* m, const uint32_t* r, uint32_t* c, long batch);
 int pai_raw_add_host(pai_pub* k, const uint32_t* a, const uint32_t* b, uint32_t* c, long batch);

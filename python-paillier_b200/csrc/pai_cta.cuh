@@ -10,6 +10,7 @@
 #include "pai_kernels.cuh"
 #include "pai_digit.cuh"
 #include "pai_rng.cuh"
+#include "pai_radix.cuh"
 
 namespace pai {
 

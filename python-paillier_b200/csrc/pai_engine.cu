@@ -87,6 +87,24 @@ struct RngBody {
       rng_fill_lt_n(key, nonce, (uint64_t)g, n, ln, nbits, out + g * ln);
   }
 };
+struct ToDecBody {
+  const uint32_t* consts; int const_quads;
+  const uint32_t* limbs; int L; uint8_t* text; int chunks; long batch;
+  PAI_MEM void run(u4* smem, const CtaId& id) const {
+    for (long g = (long)id.cta * id.nthr + id.tid; g < batch; g += (long)id.ncta * id.nthr)
+      radix_to_decimal((uint32_t*)smem, id.tid, id.nthr, limbs + g * L, L, text + g * (long)chunks * 9, chunks);
+  }
+};
+struct FromDecBody {
+  const uint32_t* consts; int const_quads;
+  const uint8_t* text; int width; uint32_t* limbs; int L; int32_t* status; long batch;
+  PAI_MEM void run(u4* smem, const CtaId& id) const {
+    for (long g = (long)id.cta * id.nthr + id.tid; g < batch; g += (long)id.ncta * id.nthr) {
+      int st = radix_from_decimal((uint32_t*)smem, id.tid, id.nthr, text + g * (long)width, width, limbs + g * L, L);
+      if (status) status[g] = st;
+    }
+  }
+};
 struct PrepBody {
   const uint32_t* consts; int const_quads;
   const uint32_t* n; const uint32_t* thresh; int ln; const uint32_t* s; uint32_t* e_out; int32_t* flag; long batch;
@@ -811,6 +829,42 @@ int pai_random_lt_n(pai_pub* k, const uint8_t* seed32, unsigned long long nonce,
   b.nonce = nonce; b.n = k->d_nth; b.ln = k->ln; b.nbits = bit_length(k->h_n); b.out = d_r; b.batch = batch;
   long blocks = (batch + 127) / 128;
   return rt_launch(b, (int)std::min(blocks, (long)rt_sm_count(k->nsq->device) * 16), 128, 0, (rt_stream)stream);
+}
+// ---- decimal wire format ---------------------------------------------------------------------
+static int radix_geometry(int device, int limbs, long batch, int* grid, int* nthr, size_t* smem) {
+  if (limbs < 1 || limbs > 1024) { g_err = "limb count not supported"; return PAI_E_ARG; }
+  int t = (int)std::min<size_t>(128, (rt_max_smem(device) - 1024) / ((size_t)limbs * 4));
+  t = std::min(t, NTHR_MAX);
+  if (t >= 32) t &= ~31;
+  if (t < 1) { g_err = "limb count not supported"; return PAI_E_ARG; }
+  *nthr = t;
+  *smem = (size_t)limbs * 4 * t;
+  *grid = (int)std::min<long>((batch + t - 1) / t, (long)rt_sm_count(device) * 8);
+  return 0;
+}
+int pai_decimal_width(int limbs) { return limbs > 0 ? 9 * radix_chunks(limbs) : 0; }
+int pai_limbs_to_decimal(const uint32_t* d_limbs, int limbs, uint8_t* d_text, long batch, int device, void* stream) {
+  DeviceGuard device_guard_; (void)device_guard_;
+  if (!d_limbs || !d_text || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  if (batch == 0) return 0;
+  int rc = rt_set_device(device);
+  if (rc) return rc;
+  int grid, nthr; size_t smem;
+  if ((rc = radix_geometry(device, limbs, batch, &grid, &nthr, &smem))) return rc;
+  ToDecBody b{nullptr, 0, d_limbs, limbs, d_text, radix_chunks(limbs), batch};
+  return rt_launch(b, grid, nthr, smem, (rt_stream)stream);
+}
+int pai_decimal_to_limbs(const uint8_t* d_text, int width, uint32_t* d_limbs, int limbs, int32_t* d_status, long batch, int device,
+                         void* stream) {
+  DeviceGuard device_guard_; (void)device_guard_;
+  if (!d_limbs || !d_text || batch < 0 || width < 1) { g_err = "bad argument"; return PAI_E_ARG; }
+  if (batch == 0) return 0;
+  int rc = rt_set_device(device);
+  if (rc) return rc;
+  int grid, nthr; size_t smem;
+  if ((rc = radix_geometry(device, limbs, batch, &grid, &nthr, &smem))) return rc;
+  FromDecBody b{nullptr, 0, d_text, width, d_limbs, limbs, d_status, batch};
+  return rt_launch(b, grid, nthr, smem, (rt_stream)stream);
 }
 int pai_raw_add(pai_pub* k, const uint32_t* d_a, const uint32_t* d_b, uint32_t* d_c, long batch, void* stream) {
   DeviceGuard device_guard_; (void)device_guard_;

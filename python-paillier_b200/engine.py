@@ -53,6 +53,9 @@ SYMBOLS = {
     "pai_pub_c_limbs": (ctypes.c_int, [_vp]),
     "pai_encrypt": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_long, _vp]),
     "pai_random_lt_n": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_ulonglong, _vp, ctypes.c_long, _vp]),
+    "pai_decimal_width": (ctypes.c_int, [ctypes.c_int]),
+    "pai_limbs_to_decimal": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_long, ctypes.c_int, _vp]),
+    "pai_decimal_to_limbs": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int, _vp, ctypes.c_long, ctypes.c_int, _vp]),
     "pai_raw_add": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_long, _vp]),
     "pai_raw_mul": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_long, _vp]),
     "pai_priv_create": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
@@ -69,6 +72,23 @@ SYMBOLS = {
     "pai_mod_powmod_host": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_long]),
     "pai_mod_invert_host": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp, ctypes.c_long]),
 }
+
+
+# ---------------------------------------------------------------------------- decimal wire format
+def limbs_to_decimal_dev(d_limbs, limbs, d_text, batch, device=0, stream=None, engine=None):
+    """d_text [batch, decimal_width(limbs)] uint8 <- decimal digits of d_limbs [batch, limbs] (pai_radix.cuh)."""
+    eng = engine or get_engine()
+    eng.check(eng.lib.pai_limbs_to_decimal(_ptr(d_limbs), limbs, _ptr(d_text), batch, device, _ptr(stream)))
+
+
+def decimal_to_limbs_dev(d_text, width, d_limbs, limbs, d_status, batch, device=0, stream=None, engine=None):
+    eng = engine or get_engine()
+    eng.check(eng.lib.pai_decimal_to_limbs(_ptr(d_text), width, _ptr(d_limbs), limbs, _ptr(d_status), batch, device,
+                                           _ptr(stream)))
+
+
+def decimal_width(limbs, engine=None):
+    return int((engine or get_engine()).lib.pai_decimal_width(limbs))
 
 
 # ---------------------------------------------------------------------------- limb packing

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 from .encoding import EncodedNumber
-from .engine import ints_to_limbs, limbs_to_ints
+from .engine import ints_to_limbs, limbs_to_ints, limbs_to_decimal_dev, decimal_to_limbs_dev, decimal_width
 
 
 def _torch():
@@ -29,6 +29,40 @@ def _to_dev(arr, ctx):
 
 def _to_host(t):
     return t.cpu().numpy().view(np.uint32)
+
+
+def limbs_to_decimal_strings(ctx, d_limbs):
+    """Device limb matrix -> list of decimal strings (str(int) of every row), converted on the GPU."""
+    torch = _torch()
+    count, limbs = int(d_limbs.shape[0]), int(d_limbs.shape[1])
+    if not count:
+        return []
+    width = decimal_width(limbs, ctx.eng)
+    d_text = torch.empty((count, width), dtype=torch.uint8, device=d_limbs.device)
+    limbs_to_decimal_dev(d_limbs, limbs, d_text, count, ctx.device, engine=ctx.eng)
+    raw = d_text.cpu().numpy().tobytes()
+    return [(raw[i * width:(i + 1) * width].lstrip(b"0") or b"0").decode("ascii") for i in range(count)]
+
+
+def decimal_strings_to_limbs(ctx, strings, limbs):
+    """List of decimal strings -> device limb matrix [len, limbs] (int() of every string, on the GPU).
+    ValueError for anything that is not a non-negative decimal integer fitting `limbs` limbs."""
+    torch = _torch()
+    count = len(strings)
+    width = max([len(t) for t in strings] + [1])
+    raw = b"".join(t.encode("ascii").rjust(width, b"0") if isinstance(t, str) else bytes(t).rjust(width, b"0") for t in strings)
+    text = np.frombuffer(raw, dtype=np.uint8).reshape(count, width)
+    t = torch.from_numpy(text.copy())
+    d_text = t if ctx.eng.simulated else t.to("cuda:%d" % ctx.device)
+    d_limbs = torch.empty((count, limbs), dtype=torch.int32, device=d_text.device)
+    d_status = torch.zeros((count,), dtype=torch.int32, device=d_text.device)
+    if count:
+        decimal_to_limbs_dev(d_text, width, d_limbs, limbs, d_status, count, ctx.device, engine=ctx.eng)
+        bad = torch.nonzero(d_status).flatten()
+        if bad.numel():
+            i = int(bad[0])
+            raise ValueError("value %d is not a decimal integer below 2**%d" % (i, 32 * limbs))
+    return d_limbs
 
 
 def random_r_values(n, count):
@@ -361,9 +395,11 @@ class EncryptedVector(object):
     def to_json(self, be_secure=True):
         """The reference's basic JSON scheme (docs/serialisation.rst:24-31): {'public_key': {'n': ...},
         'values': [[str(ciphertext), exponent], ...]} -- readable by an unmodified phe peer."""
-        import json
-        return json.dumps({"public_key": {"n": self.public_key.n},
-                           "values": [(str(c), int(e)) for c, e in zip(self.ciphertexts(be_secure), self.exponents)]})
+        if be_secure and not self._obfuscated:
+            self.obfuscate()
+        texts = limbs_to_decimal_strings(self.public_key.engine_context(), self.limbs)
+        return '{"public_key": {"n": %d}, "values": [%s]}' % (
+            self.public_key.n, ", ".join('["%s", %d]' % (t, e) for t, e in zip(texts, self.exponents.tolist())))
 
     @classmethod
     def from_json(cls, serialised, public_key=None):
@@ -375,8 +411,12 @@ class EncryptedVector(object):
         if pk.n != int(d["public_key"]["n"]):
             raise ValueError("serialised vector was encrypted against a different key")
         ctx = pk.engine_context()
-        cts = [int(v[0]) % pk.nsquare for v in d["values"]]
-        return cls(pk, _to_dev(ints_to_limbs(cts, ctx.c_limbs), ctx), [int(v[1]) for v in d["values"]])
+        texts = [str(v[0]).lstrip("0") or "0" for v in d["values"]]
+        bound = str(pk.nsquare)                    # the reference accepts any int; keep rows canonical (< n^2)
+        texts = [t if len(t) < len(bound) or (len(t) == len(bound) and t < bound) or not t.isdigit()
+                 else str(int(t) % pk.nsquare) for t in texts]
+        d_c = decimal_strings_to_limbs(ctx, texts, ctx.c_limbs)
+        return cls(pk, d_c, [int(v[1]) for v in d["values"]])
 
     # ------------------------------------------------------------------ decryption
     def decrypt_encoded(self, private_key):

@@ -250,3 +250,34 @@ def test_device_obfuscators(pkg, cuda_engine):
     pub.encrypt_dev(d_m, d_r2, d_c, batch)
     priv.decrypt_dev(d_c, d_d, batch)
     assert bool((d_d == d_m).all().item())
+
+
+def test_decimal_wire_format_on_gpu(pkg, cuda_engine):
+    """pai_limbs_to_decimal / pai_decimal_to_limbs at ciphertext size: equal to Python's str()/int() on a sample,
+    lossless round trip of the whole batch on the device, and the JSON scheme of docs/serialisation.rst."""
+    import importlib
+    import torch
+    eng = importlib.import_module("python-paillier_b200.engine")
+    n, p, q = _key(2048)
+    pub = pkg.PublicContext(n)
+    batch, lc = 20000, pub.c_limbs
+    c = _rand_rows(np.random.default_rng(3), batch, lc, lc)
+    c[0] = 0
+    c[1] = 0xffffffff
+    c[2, 1:] = 0
+    d_c = torch.from_numpy(c.view(np.int32)).cuda()
+    width = eng.decimal_width(lc)
+    d_text = torch.empty((batch, width), dtype=torch.uint8, device="cuda")
+    eng.limbs_to_decimal_dev(d_c, lc, d_text, batch)
+    d_back = torch.empty_like(d_c)
+    d_status = torch.ones((batch,), dtype=torch.int32, device="cuda")
+    eng.decimal_to_limbs_dev(d_text, width, d_back, lc, d_status, batch)
+    assert bool((d_back == d_c).all().item()) and not bool(d_status.any().item())
+    text = d_text[:200].cpu().numpy()
+    assert [bytes(r).decode() for r in text] == [str(v).rjust(width, "0") for v in pkg.limbs_to_ints(c[:200])]
+    pk = pkg.PaillierPublicKey(n)
+    sk = pkg.PaillierPrivateKey(pk, p, q)
+    v = pk.encrypt_batch([0.5 * i for i in range(-50, 50)])
+    back = pkg.EncryptedVector.from_json(v.to_json())
+    assert back.ciphertexts(False) == v.ciphertexts(False)
+    assert sk.decrypt_batch(back) == [0.5 * i for i in range(-50, 50)]
