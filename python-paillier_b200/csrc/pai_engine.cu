@@ -910,7 +910,7 @@ int pai_priv_create(const uint32_t* p, const uint32_t* q, int limbs, int device,
   int ep = eff_limbs(p, limbs), eq = eff_limbs(q, limbs);
   if (!ep || !eq || !(p[0] & 1u) || !(q[0] & 1u)) { g_err = "p and q must be odd"; return PAI_E_ARG; }
   int ntp = pick_ntp((std::max(ep, eq) + 7) / 8);
-  if (ntp < 0) { g_err = "key too large (max 4096 bits)"; return PAI_E_ARG; }
+  if (ntp < 0) { g_err = "key too large (p and q at most 2048 bits each)"; return PAI_E_ARG; }
   const int L1 = 8 * ntp;
   limbs_t pp = padded(p, ep, L1), qq = padded(q, eq, L1);
   int c = h_cmp(pp.data(), qq.data(), L1);
