@@ -11,6 +11,7 @@
 #include "pai_digit.cuh"
 #include "pai_rng.cuh"
 #include "pai_radix.cuh"
+#include "pai_coop.cuh"
 
 namespace pai {
 
@@ -244,7 +245,7 @@ PAI_DEV void side_bind(SideC<NTP>& S, u4* base, int nwin) {
 
 template <int NTP, int W>
 PAI_DEV void cta_decrypt(u4* smem, const CtaId& id, int nwin_p, int nwin_q, const uint32_t* c, uint32_t* out, long batch, u4* tbl,
-                         unsigned long long* counter) {
+                         unsigned long long* counter, const uint32_t* pre_p = nullptr, const uint32_t* pre_q = nullptr) {
   SideC<NTP> P, Qs;
   side_bind<NTP>(P, smem, nwin_p);
   side_bind<NTP>(Qs, smem + side_quads<NTP>(), nwin_q);
@@ -258,7 +259,8 @@ PAI_DEV void cta_decrypt(u4* smem, const CtaId& id, int nwin_p, int nwin_q, cons
   for (long g = sched_next_row(sched, id); g >= 0; g = sched_next_row(sched, id)) {
     bool store = g < batch;
     if (!store) g = batch - 1;
-    prog_decrypt<NTP, W>(E, P, Qs, pinvqM, c + g * lc, out + g * ln, store);
+    prog_decrypt<NTP, W>(E, P, Qs, pinvqM, c + g * lc, out + g * ln, store, pre_p ? pre_p + g * ln : nullptr,
+                         pre_q ? pre_q + g * ln : nullptr);
   }
 }
 

@@ -87,6 +87,38 @@ struct RngBody {
       rng_fill_lt_n(key, nonce, (uint64_t)g, n, ln, nbits, out + g * ln);
   }
 };
+// ---- warp-per-ciphertext bodies (pai_coop.cuh): small batches
+template <int K>
+struct CoopPowBody {
+  const uint32_t* consts; int const_quads;
+  int nsides;                               // 1, or 2 = both CRT halves of one ciphertext on two warps
+  const uint32_t* blob[2]; uint32_t n0inv[2]; const uint32_t* e[2]; int e_limbs; int nwin[2]; uint32_t* out[2];
+  const uint32_t* base; int base_limbs; int out_limbs; long batch;
+  PAI_MEM void run(u4* smem, const CtaId& id) const {
+    const int warp = id.tid >> 5, nwarp = id.nthr >> 5;
+    uint32_t* tbl = (uint32_t*)smem + (size_t)warp * ((1 << COOP_W) * K * 32);
+    const long items = batch * nsides;
+    for (long it = (long)id.cta * nwarp + warp; it < items; it += (long)id.ncta * nwarp) {
+      const int sd = (int)(it % nsides);
+      const long g = it / nsides;
+      coop_powmod<K>(blob[sd], n0inv[sd], base + g * base_limbs, base_limbs, e[sd], e_limbs, nwin[sd],
+                     out[sd] + g * out_limbs, out_limbs, tbl);
+    }
+  }
+};
+template <int K>
+struct CoopEncBody {
+  const uint32_t* consts; int const_quads;
+  const uint32_t* blob; uint32_t n0inv; const uint32_t* nrow; int n_limbs; int nwin;
+  const uint32_t* m; const uint32_t* r; uint32_t* out; long batch;
+  PAI_MEM void run(u4* smem, const CtaId& id) const {
+    const int warp = id.tid >> 5, nwarp = id.nthr >> 5;
+    uint32_t* tbl = (uint32_t*)smem + (size_t)warp * ((1 << COOP_W) * K * 32);
+    for (long g = (long)id.cta * nwarp + warp; g < batch; g += (long)id.ncta * nwarp)
+      coop_encrypt<K>(blob, n0inv, nrow, n_limbs, nrow, nwin, m + g * n_limbs, r + g * n_limbs, out + g * 2 * n_limbs,
+                      2 * n_limbs, tbl);
+  }
+};
 struct ToDecBody {
   const uint32_t* consts; int const_quads;
   const uint32_t* limbs; int L; uint8_t* text; int chunks; long batch;
@@ -116,7 +148,10 @@ template <int NTP, int W>
 struct DecBody {
   const uint32_t* consts; int const_quads;
   int nwin_p, nwin_q; const uint32_t* c; uint32_t* out; long batch; u4* tbl; unsigned long long* counter;
-  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_decrypt<NTP, W>(smem, id, nwin_p, nwin_q, c, out, batch, tbl, counter); }
+  const uint32_t* pre_p; const uint32_t* pre_q;      // c^(p-1) mod p^2, c^(q-1) mod q^2 already computed (pai_coop.cuh), or null
+  PAI_MEM void run(u4* smem, const CtaId& id) const {
+    cta_decrypt<NTP, W>(smem, id, nwin_p, nwin_q, c, out, batch, tbl, counter, pre_p, pre_q);
+  }
 };
 template <int NTP, int W>
 struct DecDigitBody {
@@ -297,6 +332,8 @@ struct pai_mod {
   limbs_t h_N;                      // padded modulus
   DevBuf tbl, tmp_a, tmp_b, tmp_o, tmp_s, tmp_e;
   Counters ctr;
+  // warp-per-ciphertext layout (pai_coop.cuh), built on first use: [ N | R^2 mod N | R^3 mod N ], R = 2^(32*32*coopK)
+  uint32_t* d_coop = nullptr; int coopK = 0; uint32_t coop_n0inv = 0; bool coop_building = false;
 };
 struct pai_pub {
   pai_mod* nsq = nullptr;           // modulus n^2; its blob is followed by n (4*NT limbs) for encrypt
@@ -321,9 +358,21 @@ struct pai_priv {
   limbs_t h_p, h_q, h_pinv, h_hp, h_hq;   // 16*NTP limbs each (padded)
   DevBuf tbl, h_c, h_m;
   Counters ctr;
+  uint32_t* d_coop_e = nullptr;     // [ p - 1 | q - 1 ] (8*NTP limbs each) for the warp-per-ciphertext path
+  DevBuf coop_u;                    // its two half results per ciphertext
 };
 
 // ------------------------------------------------------------------------------------------------
+#define DISPATCH_K(KV, CALL)                                                                          \
+  switch (KV) {                                                                                       \
+    case 1: { constexpr int K = 1; CALL; } break;                                                     \
+    case 2: { constexpr int K = 2; CALL; } break;                                                     \
+    case 3: { constexpr int K = 3; CALL; } break;                                                     \
+    case 4: { constexpr int K = 4; CALL; } break;                                                     \
+    case 6: { constexpr int K = 6; CALL; } break;                                                     \
+    case 8: { constexpr int K = 8; CALL; } break;                                                     \
+    default: g_err = "unsupported operand size"; rc = PAI_E_ARG;                                      \
+  }
 #define DISPATCH_NT(NTV, CALL)                                                                        \
   switch (NTV) {                                                                                      \
     case 1: { constexpr int NT = 1; CALL; } break;                                                    \
@@ -401,6 +450,7 @@ void mod_free(pai_mod* m) {
   if (!m) return;
   rt_set_device(m->device);
   rt_free(m->d_blob);
+  if (m->d_coop) { rt_memset(m->d_coop, 0, (size_t)3 * 32 * m->coopK * 4, 0); rt_sync(0); rt_free(m->d_coop); }
   m->ctr.buf.release(); m->tbl.release(); m->tmp_a.release(); m->tmp_b.release(); m->tmp_o.release(); m->tmp_s.release(); m->tmp_e.release();
   delete m;
 }
@@ -507,7 +557,8 @@ int do_powmod_digit(pai_pub* k, const uint32_t* base, const uint32_t* d_exp, int
 }
 
 template <int NTP>
-int do_decrypt(pai_priv* k, const uint32_t* c, uint32_t* out, long batch, rt_stream s) {
+int do_decrypt(pai_priv* k, const uint32_t* c, uint32_t* out, long batch, rt_stream s, const uint32_t* pre_p = nullptr,
+               const uint32_t* pre_q = nullptr) {
   typedef DecBody<NTP, W_DEC> B;
   Geom g;
   int cq = 2 * (mc_limbs(2 * NTP) / 4 + mc_limbs(NTP) / 4 + 6 * NTP) + 2 * NTP;
@@ -518,7 +569,7 @@ int do_decrypt(pai_priv* k, const uint32_t* c, uint32_t* out, long batch, rt_str
   unsigned long long* ctr = nullptr;
   rc = k->ctr.take(s, &ctr);
   if (rc) return rc;
-  B body{k->d_consts, cq, k->nwin_p, k->nwin_q, c, out, batch, (u4*)k->tbl.p, ctr};
+  B body{k->d_consts, cq, k->nwin_p, k->nwin_q, c, out, batch, (u4*)k->tbl.p, ctr, pre_p, pre_q};
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
 }
 
@@ -670,6 +721,90 @@ int do_priv_setup(pai_priv* k, rt_stream s) {
 }  // namespace
 
 // ================================================================================================ C ABI
+// ---- warp-per-ciphertext path (pai_coop.cuh) -------------------------------------------------------------------
+// Batches of at most coop_max() elements take it: PAI_COOP_MAX overrides the default (0 disables).
+static long coop_max() {
+  const char* e = getenv("PAI_COOP_MAX");
+  if (e && *e) return atol(e);
+#ifdef PAI_HOSTSIM
+  return 0;            // the simulation build of the tests exercises the throughput kernels unless asked otherwise
+#else
+  return 1024;
+#endif
+}
+static int coop_geometry(int device, int K, long items, int* grid, size_t* smem) {
+  *smem = (size_t)COOP_WARPS * (1 << COOP_W) * K * 32 * 4;
+  *grid = (int)std::min<long>((items + COOP_WARPS - 1) / COOP_WARPS, (long)rt_sm_count(device) * 16);
+  return 0;
+}
+// constants of the modulus in the warp layout, computed once with the generic kernels: 2^(64 Lc) and 2^(96 Lc) mod N
+static int ensure_coop(pai_mod* m, rt_stream s) {
+  if (m->d_coop) return 0;
+  const int Lc = (m->L + 31) / 32 * 32, K = Lc / 32;
+  if (K != 1 && K != 2 && K != 3 && K != 4 && K != 6 && K != 8) { g_err = "unsupported operand size"; return PAI_E_ARG; }
+  uint32_t* blob = nullptr;
+  uint32_t* tmp = nullptr;
+  int rc = rt_malloc((void**)&blob, (size_t)3 * Lc * 4);
+  if (!rc) rc = rt_malloc((void**)&tmp, (size_t)2 * m->L * 4);
+  if (!rc) rc = rt_memset(blob, 0, (size_t)3 * Lc * 4, s);
+  if (!rc) rc = rt_h2d(blob, m->h_N.data(), (size_t)m->L * 4, s);
+  limbs_t two(m->L, 0);
+  two[0] = 2;
+  if (!rc) rc = rt_h2d(tmp, two.data(), (size_t)m->L * 4, s);
+  m->coop_building = true;
+  for (int i = 0; i < 2 && !rc; i++) {
+    uint32_t e = (uint32_t)((i + 2) * 32 * Lc);
+    rc = pai_mod_powmod_shared(m, tmp, m->L, &e, 1, tmp + m->L, 1, s);
+    if (!rc) rc = rt_d2d(blob + (size_t)(i + 1) * Lc, tmp + m->L, (size_t)m->L * 4, s);
+  }
+  m->coop_building = false;
+  if (!rc) rc = rt_sync(s);
+  rt_free(tmp);
+  if (rc) { rt_free(blob); return rc; }
+  uint32_t n0 = m->h_N[0], i0 = n0;
+  for (int i = 0; i < 5; i++) i0 *= 2u - n0 * i0;
+  m->coop_n0inv = 0u - i0;
+  m->coopK = K;
+  m->d_coop = blob;
+  return 0;
+}
+template <int K>
+static int do_coop_powmod(pai_mod* m, const uint32_t* d_base, int base_limbs, const uint32_t* d_exp, int exp_limbs, int nbits,
+                          uint32_t* d_out, long batch, rt_stream s) {
+  CoopPowBody<K> b;
+  b.consts = nullptr; b.const_quads = 0; b.nsides = 1;
+  b.blob[0] = b.blob[1] = m->d_coop; b.n0inv[0] = b.n0inv[1] = m->coop_n0inv;
+  b.e[0] = b.e[1] = d_exp; b.e_limbs = exp_limbs; b.nwin[0] = b.nwin[1] = (nbits + COOP_W - 1) / COOP_W;
+  b.out[0] = b.out[1] = d_out; b.base = d_base; b.base_limbs = base_limbs; b.out_limbs = m->L; b.batch = batch;
+  int grid; size_t smem;
+  coop_geometry(m->device, K, batch, &grid, &smem);
+  return rt_launch_coop(b, grid, 32 * COOP_WARPS, smem, s);
+}
+
+template <int K>
+static int do_coop_encrypt(pai_pub* k, const uint32_t* d_m, const uint32_t* d_r, uint32_t* d_c, long batch, rt_stream s) {
+  pai_mod* m = k->nsq;
+  const int nwin = (bit_length(k->h_n) + COOP_W - 1) / COOP_W;
+  CoopEncBody<K> b{nullptr, 0, m->d_coop, m->coop_n0inv, k->d_nth, k->ln, nwin, d_m, d_r, d_c, batch};
+  int grid; size_t smem;
+  coop_geometry(m->device, K, batch, &grid, &smem);
+  return rt_launch_coop(b, grid, 32 * COOP_WARPS, smem, s);
+}
+template <int K>
+static int do_coop_decrypt_pow(pai_priv* k, const uint32_t* d_c, uint32_t* up, uint32_t* uq, long batch, rt_stream s) {
+  const int L1 = 8 * k->NTP, L2 = 16 * k->NTP;
+  CoopPowBody<K> b;
+  b.consts = nullptr; b.const_quads = 0; b.nsides = 2;
+  b.blob[0] = k->p2->d_coop; b.blob[1] = k->q2->d_coop; b.n0inv[0] = k->p2->coop_n0inv; b.n0inv[1] = k->q2->coop_n0inv;
+  b.e[0] = k->d_coop_e; b.e[1] = k->d_coop_e + L1; b.e_limbs = L1;
+  b.nwin[0] = (bit_length(h_sub_small(k->h_p, 1)) + COOP_W - 1) / COOP_W;
+  b.nwin[1] = (bit_length(h_sub_small(k->h_q, 1)) + COOP_W - 1) / COOP_W;
+  b.out[0] = up; b.out[1] = uq; b.base = d_c; b.base_limbs = 2 * L2; b.out_limbs = L2; b.batch = batch;
+  int grid; size_t smem;
+  coop_geometry(k->device, K, 2 * batch, &grid, &smem);
+  return rt_launch_coop(b, grid, 32 * COOP_WARPS, smem, s);
+}
+
 extern "C" {
 
 const char* pai_last_error(void) { return g_err.c_str(); }
@@ -715,6 +850,14 @@ int pai_mod_powmod_shared(pai_mod* m, const uint32_t* d_base, int base_limbs, co
   if (!rc) rc = rt_h2d(m->tmp_e.p, exponent, (size_t)exp_limbs * 4, (rt_stream)stream);
   if (!rc) rc = rt_sync((rt_stream)stream);   // `exponent` is caller-owned host memory
   if (rc) return rc;
+  if (!m->coop_building && batch <= coop_max()) {
+    if (base_limbs != m->L && base_limbs != 2 * m->L) { g_err = "base_limbs must be L or 2L"; return PAI_E_ARG; }
+    rc = ensure_coop(m, (rt_stream)stream);
+    if (rc) return rc;
+    DISPATCH_K(m->coopK, rc = do_coop_powmod<K>(m, d_base, base_limbs, (const uint32_t*)m->tmp_e.p, exp_limbs, bit_length(e), d_out,
+                                                batch, (rt_stream)stream));
+    return rc;
+  }
   return powmod_common(m, d_base, base_limbs, (const uint32_t*)m->tmp_e.p, exp_limbs, 0, nwin, d_out, batch, stream);
 }
 
@@ -813,6 +956,13 @@ int pai_encrypt(pai_pub* k, const uint32_t* d_m, const uint32_t* d_r, uint32_t* 
   if (batch == 0) return 0;
   int rc = rt_set_device(k->nsq->device);
   if (rc) return rc;
+  if (batch <= coop_max()) {                       // small batch: one warp per ciphertext (pai_coop.cuh)
+    pai_mod* m = k->nsq;
+    rc = ensure_coop(m, (rt_stream)stream);
+    if (rc) return rc;
+    DISPATCH_K(m->coopK, rc = do_coop_encrypt<K>(k, d_m, d_r, d_c, batch, (rt_stream)stream));
+    return rc;
+  }
   if (k->use_digit) { DISPATCH_NTH(k->nmod->NT, rc = do_encrypt_digit<NTH>(k, d_m, d_r, d_c, batch, (rt_stream)stream)); }
   else { DISPATCH_NT(k->nsq->NT, rc = do_encrypt<NT>(k, d_m, d_r, d_c, batch, (rt_stream)stream)); }
   return rc;
@@ -946,6 +1096,8 @@ int pai_priv_destroy(pai_priv* k) {
     rt_sync(0);
   }
   rt_free(k->d_dconsts);
+  if (k->d_coop_e) { rt_memset(k->d_coop_e, 0, (size_t)16 * k->NTP * 4, 0); rt_sync(0); rt_free(k->d_coop_e); }
+  k->coop_u.release();
   mod_free(k->pd); mod_free(k->qd);
   k->ctr.buf.release(); k->tbl.release(); k->h_c.release(); k->h_m.release();
   mod_free(k->p2); mod_free(k->q2); mod_free(k->p1); mod_free(k->q1);
@@ -973,6 +1125,29 @@ int pai_decrypt(pai_priv* k, const uint32_t* d_c, uint32_t* d_m, long batch, voi
   if (batch == 0) return 0;
   int rc = rt_set_device(k->device);
   if (rc) return rc;
+  if (batch <= coop_max()) {
+    // both big exponentiations on one warp each (pai_coop.cuh), then L, h and the CRT in the thread-per-ciphertext form
+    rt_stream s = (rt_stream)stream;
+    const int L1 = 8 * k->NTP, L2 = 16 * k->NTP;
+    rc = ensure_coop(k->p2, s);
+    if (!rc) rc = ensure_coop(k->q2, s);
+    if (!rc && !k->d_coop_e) {
+      limbs_t e = h_sub_small(k->h_p, 1), eq = h_sub_small(k->h_q, 1);
+      e.resize(L1, 0); eq.resize(L1, 0);
+      e.insert(e.end(), eq.begin(), eq.end());
+      rc = rt_malloc((void**)&k->d_coop_e, (size_t)2 * L1 * 4);
+      if (!rc) rc = rt_h2d(k->d_coop_e, e.data(), (size_t)2 * L1 * 4, s);
+      if (!rc) rc = rt_sync(s);
+    }
+    if (!rc) rc = k->coop_u.ensure((size_t)2 * batch * L2 * 4);
+    if (rc) return rc;
+    uint32_t* up = (uint32_t*)k->coop_u.p;
+    uint32_t* uq = up + (size_t)batch * L2;
+    DISPATCH_K(k->p2->coopK, rc = do_coop_decrypt_pow<K>(k, d_c, up, uq, batch, s));
+    if (rc) return rc;
+    DISPATCH_NTP(k->NTP, rc = do_decrypt<NTP>(k, d_c, d_m, batch, s, up, uq));
+    return rc;
+  }
   if (k->use_digit) { DISPATCH_NTP(k->NTP, rc = do_decrypt_digit<NTP>(k, d_c, d_m, batch, (rt_stream)stream)); }
   else { DISPATCH_NTP(k->NTP, rc = do_decrypt<NTP>(k, d_c, d_m, batch, (rt_stream)stream)); }
   return rc;

@@ -335,21 +335,27 @@ struct SideC {
 
 // one CRT half: out_small (NTP tiles, in buf[ret]) = L(c^(x-1) mod x^2) * h mod x
 template <int NTP, int W>
-PAI_DEV int decrypt_half(PowEnv<2 * NTP>& E, const SideC<NTP>& S, const uint32_t* c_row) {
+PAI_DEV int decrypt_half(PowEnv<2 * NTP>& E, const SideC<NTP>& S, const uint32_t* c_row, const uint32_t* pre_row = nullptr) {
   const int NT2 = 2 * NTP;
   const ModC& mq = S.sq;
-  // c mod x^2 in Montgomery form: c = lo + hi*R  ->  lo*R + hi*R^2   (GMP reduces the base the same way)
-  load_row(E.buf[0], c_row, 2 * NT2, 2 * NT2);
-  mont_mul<NT2>(E.buf[2], E.buf[0], mq.R2, mq.N, mq.ninv);
-  load_row(E.buf[0], c_row + 8 * NT2, 2 * NT2, 2 * NT2);
-  mont_mul<NT2>(E.buf[1], E.buf[0], mq.R3, mq.N, mq.ninv);
-  uint32_t cy = big_add_masked<NT2>(E.buf[1], E.buf[1], E.buf[2], 0xffffffffu);
-  big_cond_sub<NT2>(E.buf[1], mq.N, cy);
-  E.mc = const_cast<ModC*>(&S.sq);
-  int cur = mont_pow<NT2, W, false>(E, 1, S.e, 8 * NTP, S.nwin);          // c^(x-1) * R mod x^2
-  int a = cur == 2 ? 0 : cur + 1;
-  int b = a == 2 ? 0 : a + 1;
-  mont_mul<NT2>(E.buf[a], E.buf[cur], mq.ONE, mq.N, mq.ninv);             // u = c^(x-1) mod x^2
+  int a, b;
+  if (pre_row) {                                                           // u = c^(x-1) mod x^2 computed elsewhere
+    a = 1; b = 2;
+    load_row(E.buf[a], pre_row, 2 * NT2, 2 * NT2);
+  } else {
+    // c mod x^2 in Montgomery form: c = lo + hi*R  ->  lo*R + hi*R^2   (GMP reduces the base the same way)
+    load_row(E.buf[0], c_row, 2 * NT2, 2 * NT2);
+    mont_mul<NT2>(E.buf[2], E.buf[0], mq.R2, mq.N, mq.ninv);
+    load_row(E.buf[0], c_row + 8 * NT2, 2 * NT2, 2 * NT2);
+    mont_mul<NT2>(E.buf[1], E.buf[0], mq.R3, mq.N, mq.ninv);
+    uint32_t cy = big_add_masked<NT2>(E.buf[1], E.buf[1], E.buf[2], 0xffffffffu);
+    big_cond_sub<NT2>(E.buf[1], mq.N, cy);
+    E.mc = const_cast<ModC*>(&S.sq);
+    int cur = mont_pow<NT2, W, false>(E, 1, S.e, 8 * NTP, S.nwin);        // c^(x-1) * R mod x^2
+    a = cur == 2 ? 0 : cur + 1;
+    b = a == 2 ? 0 : a + 1;
+    mont_mul<NT2>(E.buf[a], E.buf[cur], mq.ONE, mq.N, mq.ninv);           // u = c^(x-1) mod x^2
+  }
   // L(u) = (u - 1) // x.  u = 1 mod x whenever gcd(c, x) = 1, so the division is exact and equals
   // (u-1) * x^-1 mod 2^(256 NTP).  Otherwise x | c and u == 0: Python's floor division gives
   // (0-1)//x = -1, which the following mulmod(., h, x) sees as x - 1.
@@ -375,11 +381,12 @@ PAI_DEV int decrypt_half(PowEnv<2 * NTP>& E, const SideC<NTP>& S, const uint32_t
 // out_row (2*NTP tiles = limbs of n) doubles as the spill slot for m_p between the halves.
 template <int NTP, int W>
 PAI_DEV void prog_decrypt(PowEnv<2 * NTP>& E, const SideC<NTP>& P, const SideC<NTP>& Qs, const Opnd& pinvqM,
-                          const uint32_t* c_row, uint32_t* out_row, bool store) {
+                          const uint32_t* c_row, uint32_t* out_row, bool store, const uint32_t* pre_p = nullptr,
+                          const uint32_t* pre_q = nullptr) {
   const int NT2 = 2 * NTP;
-  int ip = decrypt_half<NTP, W>(E, P, c_row);
+  int ip = decrypt_half<NTP, W>(E, P, c_row, pre_p);
   if (store) store_row(out_row, E.buf[ip], 2 * NTP);                      // m_p -> global (low half)
-  int iq = decrypt_half<NTP, W>(E, Qs, c_row);
+  int iq = decrypt_half<NTP, W>(E, Qs, c_row, pre_q);
   int a = iq == 2 ? 0 : iq + 1;
   int b = a == 2 ? 0 : a + 1;
   if (store) load_row(E.buf[a], out_row, 2 * NTP, 2 * NTP);

@@ -88,6 +88,10 @@ static inline int rt_launch(const Body& b, int grid, int nthr, size_t smem, rt_s
   return 0;
 }
 
+// warp-cooperative bodies (pai_coop.cuh): every thread runs the body, lanes cooperate through shuffles
+template <class Body>
+static inline int rt_launch_coop(const Body& b, int grid, int nthr, size_t smem, rt_stream s) { return rt_launch(b, grid, nthr, smem, s); }
+
 #else
 // ------------------------------------------------------------------------------------ host simulation (tests only)
 typedef void* rt_stream;
@@ -113,6 +117,15 @@ static inline int rt_launch(const Body& b, int grid, int nthr, size_t smem, rt_s
     for (int tid = 0; tid < nthr; tid++) { CtaId id{tid, nthr, cta, grid}; cta_load_consts(sm.data(), id, b.consts, b.const_quads); }
     for (int tid = 0; tid < nthr; tid++) { CtaId id{tid, nthr, cta, grid}; b.run(sm.data(), id); }
   }
+  g_launches++;
+  return 0;
+}
+// warp-cooperative bodies: one call per warp walks its 32 lanes in lockstep (lane arrays, pai_coop.cuh)
+template <class Body>
+static inline int rt_launch_coop(const Body& b, int grid, int nthr, size_t smem, rt_stream) {
+  std::vector<u4> sm(smem / 16 + 1);
+  for (int cta = 0; cta < grid; cta++)
+    for (int warp = 0; warp < nthr / 32; warp++) { CtaId id{warp * 32, nthr, cta, grid}; b.run(sm.data(), id); }
   g_launches++;
   return 0;
 }

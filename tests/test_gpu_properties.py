@@ -101,8 +101,11 @@ def test_homomorphism_add_mul_at_scale(pkg, cuda_engine, gmp):
     assert ct == [orc.raw_mul(opub, x, int(kv[i])) for x, i in zip(ca, idx)]
 
 
-def test_negative_scalars_and_ragged_batches(pkg, cuda_engine, gmp):
-    """_raw_mul's inverse branch at 2048 bit, empty / 1 / non-multiple-of-warp batches."""
+@pytest.mark.parametrize("coop_max", ["0", "1024"])
+def test_negative_scalars_and_ragged_batches(pkg, cuda_engine, gmp, monkeypatch, coop_max):
+    """_raw_mul's inverse branch at 2048 bit, empty / 1 / non-multiple-of-warp batches, on the thread-per-ciphertext
+    kernels (PAI_COOP_MAX=0) and on the warp-per-ciphertext ones."""
+    monkeypatch.setenv("PAI_COOP_MAX", coop_max)
     n, p, q = _key(2048)
     pub, priv = pkg.PublicContext(n), pkg.PrivateContext(p, q)
     opub = orc.PublicConsts(n)
@@ -195,16 +198,17 @@ def test_streams_and_cuda_graph(pkg, cuda_engine, gmp):
 
 
 def test_all_kernel_paths_agree(pkg, cuda_engine, monkeypatch):
-    """The base-n digit kernels (default) and the full-width Montgomery kernels (PAI_*_PATH=full) must give
-    identical bits."""
+    """The base-n digit kernels (default), the full-width Montgomery kernels (PAI_*_PATH=full) and the
+    warp-per-ciphertext kernels (small batches, pai_coop.cuh) must give identical bits."""
     n, p, q = _key(1024)
     rng = random.Random(21)
     m = [rng.randrange(n) for _ in range(300)] + [0, 1, n - 1]
     r = [rng.randrange(1, n) for _ in m]
     k = [rng.getrandbits(64) for _ in m[:150]] + [n - 1 - rng.getrandbits(40) for _ in m[150:]]
     results = []
-    for env in ({}, {"PAI_ENCRYPT_PATH": "full", "PAI_DECRYPT_PATH": "full"}):
-        for key in ("PAI_ENCRYPT_PATH", "PAI_DECRYPT_PATH"):
+    for env in ({"PAI_COOP_MAX": "0"}, {"PAI_ENCRYPT_PATH": "full", "PAI_DECRYPT_PATH": "full", "PAI_COOP_MAX": "0"},
+                {"PAI_COOP_MAX": "100000"}):
+        for key in ("PAI_ENCRYPT_PATH", "PAI_DECRYPT_PATH", "PAI_COOP_MAX"):
             monkeypatch.delenv(key, raising=False)
         for key, val in env.items():
             monkeypatch.setenv(key, val)
@@ -213,7 +217,7 @@ def test_all_kernel_paths_agree(pkg, cuda_engine, monkeypatch):
         t, st = pub.raw_mul(c, k)
         results.append((c, priv.raw_decrypt(c), t, st, priv.raw_decrypt(t)))
         pub.close(); priv.close()
-    assert results[0] == results[1]
+    assert results[0] == results[1] == results[2]
     assert results[0][1] == m
 
 
