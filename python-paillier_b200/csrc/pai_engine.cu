@@ -346,6 +346,7 @@ struct pai_pub {
   pai_mod* nmod = nullptr;          // modulus n with the digit-form constants appended (pai_digit.cuh)
   uint32_t* d_enc_consts = nullptr; // compact constant area of the encrypt kernel (dc_enc_limbs)
   bool use_digit = true;            // PAI_ENCRYPT_PATH=full selects the full-width Montgomery path instead
+  long wave = 0;                    // ciphertexts per wave of the throughput encrypt kernel (lazily measured)
 };
 struct pai_priv {
   int device = 0, NTP = 0;
@@ -358,6 +359,7 @@ struct pai_priv {
   limbs_t h_p, h_q, h_pinv, h_hp, h_hq;   // 16*NTP limbs each (padded)
   DevBuf tbl, h_c, h_m;
   Counters ctr;
+  long wave = 0;                    // ciphertexts per wave of the throughput decrypt kernel (lazily measured)
   uint32_t* d_coop_e = nullptr;     // [ p - 1 | q - 1 ] (8*NTP limbs each) for the warp-per-ciphertext path
   DevBuf coop_u;                    // its two half results per ciphertext
 };
@@ -538,6 +540,15 @@ int do_encrypt_digit(pai_pub* k, const uint32_t* m_, const uint32_t* r, uint32_t
   B body{k->d_enc_consts, cq, k->d_prog, k->nops, k->nodd, m_, r, c, batch, (u4*)m->tbl.p, ctr, m->d_blob + dc_zero_offset(NTH)};
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
 }
+
+template <class B>
+long wave_of(int device, int NT, int cq, int nbuf) {
+  Geom g;
+  if (geometry<B>(device, NT, cq, nbuf, 1L << 40, g)) return 0;
+  return (long)g.grid * g.nthr;
+}
+template <int NTH>
+long encrypt_wave_digit(pai_pub* k) { return wave_of<EncDigitBody<NTH>>(k->nmod->device, 2 * NTH, dc_enc_limbs(NTH) / 4, 2); }
 
 template <int NTH>
 int do_powmod_digit(pai_pub* k, const uint32_t* base, const uint32_t* d_exp, int exp_limbs, uint32_t* out, long batch, rt_stream s) {
@@ -722,15 +733,27 @@ int do_priv_setup(pai_priv* k, rt_stream s) {
 
 // ================================================================================================ C ABI
 // ---- warp-per-ciphertext path (pai_coop.cuh) -------------------------------------------------------------------
-// Batches of at most coop_max() elements take it: PAI_COOP_MAX overrides the default (0 disables).
-static long coop_max() {
+// A batch, or the tail of a batch beyond whole waves of the throughput kernel, of at most coop_limit(wave) elements
+// takes it.  Measured at 2048-bit keys (profiles/README.md): a wave of the thread-per-ciphertext kernel costs the same
+// 220 ms (encrypt) / 69 ms (decrypt) whether it holds 1 or 33 152 ciphertexts, the warp kernels run at ~0.35x of its
+// full-wave throughput with a 20 ms / 4 ms floor -- so they win up to about a third of a wave.
+// PAI_COOP_MAX overrides the limit with an absolute element count (0 disables the path).
+static long coop_limit(long wave) {
   const char* e = getenv("PAI_COOP_MAX");
   if (e && *e) return atol(e);
 #ifdef PAI_HOSTSIM
+  (void)wave;
   return 0;            // the simulation build of the tests exercises the throughput kernels unless asked otherwise
 #else
-  return 1024;
+  return wave * 3 / 10;
 #endif
+}
+// rows [batch - n, batch) that go to the warp kernels
+static long coop_rows(long batch, long wave) {
+  const long lim = coop_limit(wave);
+  if (batch <= lim) return batch;
+  const long tail = wave > 0 ? batch % wave : 0;
+  return tail <= lim ? tail : 0;
 }
 static int coop_geometry(int device, int K, long items, int* grid, size_t* smem) {
   *smem = (size_t)COOP_WARPS * (1 << COOP_W) * K * 32 * 4;
@@ -846,14 +869,17 @@ int pai_mod_powmod_shared(pai_mod* m, const uint32_t* d_base, int base_limbs, co
   if (rc) return rc;
   limbs_t e(exponent, exponent + exp_limbs);
   int nwin = (bit_length(e) + W_VAR - 1) / W_VAR;
+  const bool coop = !m->coop_building && batch <= coop_limit(8192);
+  if (coop) {                                   // before the exponent is staged: building the constants uses tmp_e too
+    if (base_limbs != m->L && base_limbs != 2 * m->L) { g_err = "base_limbs must be L or 2L"; return PAI_E_ARG; }
+    rc = ensure_coop(m, (rt_stream)stream);
+    if (rc) return rc;
+  }
   rc = m->tmp_e.ensure((size_t)exp_limbs * 4);
   if (!rc) rc = rt_h2d(m->tmp_e.p, exponent, (size_t)exp_limbs * 4, (rt_stream)stream);
   if (!rc) rc = rt_sync((rt_stream)stream);   // `exponent` is caller-owned host memory
   if (rc) return rc;
-  if (!m->coop_building && batch <= coop_max()) {
-    if (base_limbs != m->L && base_limbs != 2 * m->L) { g_err = "base_limbs must be L or 2L"; return PAI_E_ARG; }
-    rc = ensure_coop(m, (rt_stream)stream);
-    if (rc) return rc;
+  if (coop) {
     DISPATCH_K(m->coopK, rc = do_coop_powmod<K>(m, d_base, base_limbs, (const uint32_t*)m->tmp_e.p, exp_limbs, bit_length(e), d_out,
                                                 batch, (rt_stream)stream));
     return rc;
@@ -956,12 +982,22 @@ int pai_encrypt(pai_pub* k, const uint32_t* d_m, const uint32_t* d_r, uint32_t* 
   if (batch == 0) return 0;
   int rc = rt_set_device(k->nsq->device);
   if (rc) return rc;
-  if (batch <= coop_max()) {                       // small batch: one warp per ciphertext (pai_coop.cuh)
+  if (!k->wave) {
+    if (k->use_digit) { DISPATCH_NTH(k->nmod->NT, k->wave = encrypt_wave_digit<NTH>(k)); }
+    else { DISPATCH_NT(k->nsq->NT, k->wave = (wave_of<EncBody<NT>>(k->nsq->device, NT, mc_limbs(NT) / 4 + NT, 2))); }
+    if (rc) return rc;
+    if (k->wave <= 0) k->wave = 1;
+  }
+  const long ncoop = coop_rows(batch, k->wave);     // small batch / tail: one warp per ciphertext (pai_coop.cuh)
+  if (ncoop) {
     pai_mod* m = k->nsq;
     rc = ensure_coop(m, (rt_stream)stream);
     if (rc) return rc;
-    DISPATCH_K(m->coopK, rc = do_coop_encrypt<K>(k, d_m, d_r, d_c, batch, (rt_stream)stream));
-    return rc;
+    const long off = batch - ncoop;
+    DISPATCH_K(m->coopK, rc = do_coop_encrypt<K>(k, d_m + off * k->ln, d_r + off * k->ln, d_c + off * 2 * k->ln, ncoop,
+                                                 (rt_stream)stream));
+    if (rc || off == 0) return rc;
+    batch = off;
   }
   if (k->use_digit) { DISPATCH_NTH(k->nmod->NT, rc = do_encrypt_digit<NTH>(k, d_m, d_r, d_c, batch, (rt_stream)stream)); }
   else { DISPATCH_NT(k->nsq->NT, rc = do_encrypt<NT>(k, d_m, d_r, d_c, batch, (rt_stream)stream)); }
@@ -1125,10 +1161,18 @@ int pai_decrypt(pai_priv* k, const uint32_t* d_c, uint32_t* d_m, long batch, voi
   if (batch == 0) return 0;
   int rc = rt_set_device(k->device);
   if (rc) return rc;
-  if (batch <= coop_max()) {
+  if (!k->wave) {
+    if (k->use_digit) { DISPATCH_NTP(k->NTP, k->wave = (wave_of<DecDigitBody<NTP, W_DEC>>(k->device, 2 * NTP, 2 * (dside_limbs<NTP>() / 4) + 2 * NTP, 2))); }
+    else { DISPATCH_NTP(k->NTP, k->wave = (wave_of<DecBody<NTP, W_DEC>>(k->device, 2 * NTP, 2 * (mc_limbs(2 * NTP) / 4 + mc_limbs(NTP) / 4 + 6 * NTP) + 2 * NTP, 3))); }
+    if (rc) return rc;
+    if (k->wave <= 0) k->wave = 1;
+  }
+  const long ncoop = coop_rows(batch, k->wave);
+  if (ncoop) {
     // both big exponentiations on one warp each (pai_coop.cuh), then L, h and the CRT in the thread-per-ciphertext form
     rt_stream s = (rt_stream)stream;
     const int L1 = 8 * k->NTP, L2 = 16 * k->NTP;
+    const long off = batch - ncoop;
     rc = ensure_coop(k->p2, s);
     if (!rc) rc = ensure_coop(k->q2, s);
     if (!rc && !k->d_coop_e) {
@@ -1139,14 +1183,15 @@ int pai_decrypt(pai_priv* k, const uint32_t* d_c, uint32_t* d_m, long batch, voi
       if (!rc) rc = rt_h2d(k->d_coop_e, e.data(), (size_t)2 * L1 * 4, s);
       if (!rc) rc = rt_sync(s);
     }
-    if (!rc) rc = k->coop_u.ensure((size_t)2 * batch * L2 * 4);
+    if (!rc) rc = k->coop_u.ensure((size_t)2 * ncoop * L2 * 4);
     if (rc) return rc;
     uint32_t* up = (uint32_t*)k->coop_u.p;
-    uint32_t* uq = up + (size_t)batch * L2;
-    DISPATCH_K(k->p2->coopK, rc = do_coop_decrypt_pow<K>(k, d_c, up, uq, batch, s));
+    uint32_t* uq = up + (size_t)ncoop * L2;
+    DISPATCH_K(k->p2->coopK, rc = do_coop_decrypt_pow<K>(k, d_c + off * 2 * L2, up, uq, ncoop, s));
     if (rc) return rc;
-    DISPATCH_NTP(k->NTP, rc = do_decrypt<NTP>(k, d_c, d_m, batch, s, up, uq));
-    return rc;
+    DISPATCH_NTP(k->NTP, rc = do_decrypt<NTP>(k, d_c + off * 2 * L2, d_m + off * L2, ncoop, s, up, uq));
+    if (rc || off == 0) return rc;
+    batch = off;
   }
   if (k->use_digit) { DISPATCH_NTP(k->NTP, rc = do_decrypt_digit<NTP>(k, d_c, d_m, batch, (rt_stream)stream)); }
   else { DISPATCH_NTP(k->NTP, rc = do_decrypt<NTP>(k, d_c, d_m, batch, (rt_stream)stream)); }

@@ -75,9 +75,33 @@ def test_generic_powmod_through_the_warp_path(pkg, sim, monkeypatch):
     for bits in (33, 250, 700, 1100, 2100):
         N = rng.getrandbits(bits) | (1 << (bits - 1)) | 1
         ctx = pkg.ModContext(N, engine=sim)
+        assert ctx.powmod([N - 2], 77) == [pow(N - 2, 77, N)]           # first call on a fresh context, batch of one
         for e in (0, 1, 2, 15, 16, 65537, rng.getrandbits(bits), N - 1):
             bases = [0, 1, N - 1, rng.randrange(N)]
             assert ctx.powmod(bases, e) == [pow(b, e, N) for b in bases]
         wide = [N * N - 1, (1 << (64 * ctx.limbs)) - 1, N + 1]          # double-width bases are reduced first
         assert ctx.powmod(wide, 65537) == [pow(b, 65537, N) for b in wide]
         ctx.close()
+
+
+def test_tail_of_a_batch_goes_to_the_warp_path(pkg, sim, monkeypatch):
+    """Whole waves on the throughput kernel, the remainder on the warp kernels, one call (the simulation build has
+    waves of 4 ciphertexts): results are in order and equal to the all-throughput run."""
+    fx = load_golden("vectors_256.json")
+    n, p, q = H(fx["n"]), H(fx["p"]), H(fx["q"])
+    rng = random.Random(3)
+    for batch in (5, 7, 8, 11):
+        ms = [rng.randrange(n) for _ in range(batch)]
+        rs = [rng.randrange(1, n) for _ in range(batch)]
+        outs = []
+        for lim in ("0", "3"):
+            monkeypatch.setenv("PAI_COOP_MAX", lim)
+            pub, priv = pkg.PublicContext(n, engine=sim), pkg.PrivateContext(p, q, engine=sim)
+            before = sim.lib.pai_launch_count()
+            cs = pub.raw_encrypt(ms, rs)
+            launches = sim.lib.pai_launch_count() - before
+            outs.append((cs, priv.raw_decrypt(cs), launches))
+            pub.close(); priv.close()
+        assert outs[0][:2] == outs[1][:2] and outs[0][1] == ms
+        # 0 < batch % 4 <= 3 -> two launches more than the plain run (constants of the warp layout) or at least one
+        assert (outs[1][2] > outs[0][2]) == (batch % 4 != 0)
