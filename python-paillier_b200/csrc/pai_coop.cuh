@@ -3,9 +3,9 @@
 // The throughput kernels (pai_cta.cuh) give every ciphertext one thread; a lone r^n mod n^2 then takes the full
 // ~0.2 s of a 2048-bit ladder whatever the batch size, where the reference's GMP call (phe/util.py:50) takes 9 ms.
 // Here the 32 lanes of a warp share one number: lane t holds limbs [t*K, (t+1)*K) in registers, a Montgomery
-// product is the word-serial CIOS loop with the multiplier limb broadcast by shuffle, each lane keeps a private
-// carry word between iterations (carry-save across lanes), and carries / borrows between lanes are resolved once per
-// product with ballot-terminated ripple rounds.  Window table (fixed 4-bit windows, always multiplied: the exponent
+// product is the word-serial CIOS loop with the multiplier limb broadcast by shuffle, accumulators stay in
+// carry-save form (64-bit per limb position, no carry chains inside the loop), and carries / borrows between lanes
+// are resolved once per product with ballot-terminated ripple rounds.  Window table (fixed 4-bit windows, always multiplied: the exponent
 // may be secret) in shared memory.  Same results as the thread-per-ciphertext kernels, bit for bit.
 //
 // Written over "lane arrays" x[WL][..]: WL = 1 on the GPU (plain registers, ln is always 0) and WL = 32 in the CPU
@@ -24,7 +24,8 @@ constexpr int WL = 1;
 #endif
 #define PAI_EACH_LANE for (int ln = 0; ln < WL; ln++)
 constexpr int COOP_W = 4;                 // window bits
-constexpr int COOP_WARPS = 4;             // warps (ciphertexts in flight) per CTA
+constexpr int COOP_WARPS = 1;             // warps per CTA: one, so that all control flow around the shuffles is
+                                          // block-uniform and ptxas emits them without divergence guards
 
 // ---- warp primitives over lane arrays -----------------------------------------------------------------------
 template <class T>
@@ -197,11 +198,15 @@ PAI_DEV void w_add_mod(uint32_t (&x)[WL][K], const uint32_t (&y)[WL][K], const u
 }
 
 // ---- Montgomery product: r = a * b / 2^(32*32K) mod n, a < 2^(32*32K), b < n, r < n ----------------------------
+// Word-serial CIOS in carry-save form: position k of a lane is a 64-bit accumulator that is < 2^33 whenever a row of
+// products is added (so a[k]*b + acc[k] cannot overflow: one IMAD.WIDE per product, all K independent), and the
+// high halves move up one position when the number is shifted down a limb.  The only values that cross lanes per
+// limb are the multiplier limb, the quotient limb (lane 0's low word) and the low word each lane hands down.
 template <int K>
 PAI_DEV void w_mont_mul(uint32_t (&r)[WL][K], const uint32_t (&a)[WL][K], const uint32_t (&b)[WL][K],
                         const uint32_t (&n)[WL][K], uint32_t n0inv) {
-  uint32_t acc[WL][K];
-  uint64_t sp[WL];                         // carry word of each lane: weight of the limb just above its K limbs
+  uint64_t acc[WL][K];
+  uint64_t sp[WL];                         // carry word at the position just above the lane's K limbs (small)
   PAI_EACH_LANE {
     sp[ln] = 0;
     PAI_UNROLL
@@ -210,48 +215,50 @@ PAI_DEV void w_mont_mul(uint32_t (&r)[WL][K], const uint32_t (&a)[WL][K], const 
   for (int jt = 0; jt < 32; jt++) {
     PAI_UNROLL
     for (int jk = 0; jk < K; jk++) {
-      uint32_t bsel[WL], bj[WL], a0[WL], q[WL];
+      uint32_t bsel[WL], bj[WL], a0[WL], q[WL], low[WL], nl[WL];
       PAI_EACH_LANE bsel[ln] = b[ln][jk];
       w_bcast(bj, bsel, jt);
       PAI_EACH_LANE {
-        uint64_t c = 0;
         PAI_UNROLL
-        for (int k = 0; k < K; k++) {
-          uint64_t t = (uint64_t)a[ln][k] * bj[ln] + acc[ln][k] + c;
-          acc[ln][k] = (uint32_t)t; c = t >> 32;
-        }
-        sp[ln] += c;
-        a0[ln] = acc[ln][0];
+        for (int k = 0; k < K; k++) acc[ln][k] += (uint64_t)a[ln][k] * bj[ln];
+        a0[ln] = (uint32_t)acc[ln][0];
       }
       w_bcast(q, a0, 0);
-      uint32_t low[WL], up[WL];
       PAI_EACH_LANE {
         const uint32_t qq = q[ln] * n0inv;
-        uint64_t c = 0;
+        // high halves up one position (the top one into the lane's carry word), then the quotient row
+        sp[ln] += acc[ln][K - 1] >> 32;
         PAI_UNROLL
-        for (int k = 0; k < K; k++) {
-          uint64_t t = (uint64_t)n[ln][k] * qq + acc[ln][k] + c;
-          acc[ln][k] = (uint32_t)t; c = t >> 32;
-        }
-        sp[ln] += c;
-        low[ln] = acc[ln][0];
+        for (int k = K - 1; k >= 1; k--) acc[ln][k] = (uint64_t)(uint32_t)acc[ln][k] + (acc[ln][k - 1] >> 32);
+        acc[ln][0] = (uint32_t)acc[ln][0];
+        PAI_UNROLL
+        for (int k = 0; k < K; k++) acc[ln][k] += (uint64_t)n[ln][k] * qq;
+        low[ln] = (uint32_t)acc[ln][0];
       }
-      // drop the (now zero) lowest limb: every limb moves down one position, across lanes through a shuffle
-      w_down1(up, low);
+      // lane 0's low word is zero now: every position moves down one limb, high halves up one position
+      w_down1(nl, low);
       PAI_EACH_LANE {
         PAI_UNROLL
-        for (int k = 0; k + 1 < K; k++) acc[ln][k] = acc[ln][k + 1];
-        uint64_t v = sp[ln] + up[ln];
+        for (int k = 0; k + 1 < K; k++) acc[ln][k] = (uint64_t)(uint32_t)acc[ln][k + 1] + (acc[ln][k] >> 32);
+        uint64_t v = (uint64_t)nl[ln] + (acc[ln][K - 1] >> 32) + sp[ln];
         acc[ln][K - 1] = (uint32_t)v;
         sp[ln] = v >> 32;
       }
     }
   }
-  uint32_t top = w_resolve_carries<K>(acc, sp);
-  w_cond_sub<K>(acc, top, n);
+  // positions are < 2^33: normalise inside the lane, then across lanes
+  uint32_t out[WL][K];
+  PAI_EACH_LANE {
+    uint64_t c = 0;
+    PAI_UNROLL
+    for (int k = 0; k < K; k++) { uint64_t t = acc[ln][k] + c; out[ln][k] = (uint32_t)t; c = t >> 32; }
+    sp[ln] += c;
+  }
+  uint32_t top = w_resolve_carries<K>(out, sp);
+  w_cond_sub<K>(out, top, n);
   PAI_EACH_LANE {
     PAI_UNROLL
-    for (int k = 0; k < K; k++) r[ln][k] = acc[ln][k];
+    for (int k = 0; k < K; k++) r[ln][k] = out[ln][k];
   }
 }
 
@@ -260,7 +267,7 @@ PAI_DEV void w_mont_mul(uint32_t (&r)[WL][K], const uint32_t (&a)[WL][K], const 
 template <int K>
 struct CoopC {
   uint32_t n[WL][K], rr[WL][K];
-  uint32_t n0inv;
+  uint32_t n0inv;                          // -N^-1 mod 2^32
 };
 template <int K>
 PAI_DEV void coop_bind(CoopC<K>& c, const uint32_t* blob, uint32_t n0inv) {

@@ -95,7 +95,7 @@ struct CoopPowBody {
   const uint32_t* blob[2]; uint32_t n0inv[2]; const uint32_t* e[2]; int e_limbs; int nwin[2]; uint32_t* out[2];
   const uint32_t* base; int base_limbs; int out_limbs; long batch;
   PAI_MEM void run(u4* smem, const CtaId& id) const {
-    const int warp = id.tid >> 5, nwarp = id.nthr >> 5;
+    const int warp = COOP_WARPS == 1 ? 0 : id.tid >> 5, nwarp = COOP_WARPS == 1 ? 1 : id.nthr >> 5;
     uint32_t* tbl = (uint32_t*)smem + (size_t)warp * ((1 << COOP_W) * K * 32);
     const long items = batch * nsides;
     for (long it = (long)id.cta * nwarp + warp; it < items; it += (long)id.ncta * nwarp) {
@@ -112,7 +112,7 @@ struct CoopEncBody {
   const uint32_t* blob; uint32_t n0inv; const uint32_t* nrow; int n_limbs; int nwin;
   const uint32_t* m; const uint32_t* r; uint32_t* out; long batch;
   PAI_MEM void run(u4* smem, const CtaId& id) const {
-    const int warp = id.tid >> 5, nwarp = id.nthr >> 5;
+    const int warp = COOP_WARPS == 1 ? 0 : id.tid >> 5, nwarp = COOP_WARPS == 1 ? 1 : id.nthr >> 5;
     uint32_t* tbl = (uint32_t*)smem + (size_t)warp * ((1 << COOP_W) * K * 32);
     for (long g = (long)id.cta * nwarp + warp; g < batch; g += (long)id.ncta * nwarp)
       coop_encrypt<K>(blob, n0inv, nrow, n_limbs, nrow, nwin, m + g * n_limbs, r + g * n_limbs, out + g * 2 * n_limbs,
@@ -757,7 +757,9 @@ static long coop_rows(long batch, long wave) {
 }
 static int coop_geometry(int device, int K, long items, int* grid, size_t* smem) {
   *smem = (size_t)COOP_WARPS * (1 << COOP_W) * K * 32 * 4;
-  *grid = (int)std::min<long>((items + COOP_WARPS - 1) / COOP_WARPS, (long)rt_sm_count(device) * 16);
+  // one CTA (= one warp) per item, no grid-stride loop: the hardware block scheduler refills SMs as items finish
+  (void)device;
+  *grid = (int)std::min<long>((items + COOP_WARPS - 1) / COOP_WARPS, 1L << 30);
   return 0;
 }
 // constants of the modulus in the warp layout, computed once with the generic kernels: 2^(64 Lc) and 2^(96 Lc) mod N
@@ -786,7 +788,7 @@ static int ensure_coop(pai_mod* m, rt_stream s) {
   if (rc) { rt_free(blob); return rc; }
   uint32_t n0 = m->h_N[0], i0 = n0;
   for (int i = 0; i < 5; i++) i0 *= 2u - n0 * i0;
-  m->coop_n0inv = 0u - i0;
+  m->coop_n0inv = 0u - i0;                       // -N^-1 mod 2^32
   m->coopK = K;
   m->d_coop = blob;
   return 0;
