@@ -190,6 +190,20 @@ def measured_int_peak():
         return fallback
 
 
+def _ncu_traffic(batch):
+    """DRAM bytes (read + write) of one encrypt launch of `batch` rows, from the committed `ncu --set full` capture
+    (profiles/r01_ncu_traffic.json: measured on one wave of 33 152 rows, scaled per row).  Algorithmic bytes are 1 KB
+    per encrypt; the rest is the per-thread window table spilling from L2."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        return {"bytes_per_launch": t["bytes_per_ciphertext"] * batch, "bytes_per_ciphertext": t["bytes_per_ciphertext"],
+                "algorithmic_bytes_per_ciphertext": 1024, "source": t["source"]}
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -360,7 +374,7 @@ def main():
                     "executed_frac": dec_per_s / world * executed_macs_2048()[1] / peak_mac_s},
         "hbm": {"achieved_gbs": enc_per_s / world * (ln * 2 + lc) * 4 / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,
                 "frac": enc_per_s / world * (ln * 2 + lc) * 4 / 1e9 / hbm_peak},
-        "traffic": None,
+        "traffic": _ncu_traffic(args.batch),
     }
     cpu = None
     if not args.no_cpu:
