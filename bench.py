@@ -169,7 +169,7 @@ def run_reference(args, key):
         "e2e": {"value": enc, "unit": "encrypts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # --------------------------------------------------------------------------------------------- GPU side
@@ -204,6 +204,15 @@ def _ncu_traffic(batch):
         return None
 
 
+_OUT = None
+
+
+def _emit(obj):
+    out = _OUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -216,6 +225,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: native libraries (NCCL's version banner, ...) write to fd 1 as well, so
+    # everything but the final line is sent to stderr
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     from oracle.golden import H, load_golden
     fx = load_golden("vectors_%d.json" % KEY_BITS)
@@ -396,7 +411,7 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "targets": {"encrypts_per_s_1gpu": 1e5, "decrypts_per_s_1gpu": 2e5},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
