@@ -10,12 +10,18 @@ def sim(pkg):
     return pkg.Engine(ge.build_hostsim())
 
 
-odd_moduli = st.integers(min_value=3, max_value=2 ** 700).map(lambda x: x | 1)
+@pytest.fixture(params=["thread-per-ciphertext", "warp-per-ciphertext"])
+def kernel_family(request, monkeypatch):
+    """Both kernel families behind the same entry points (PAI_COOP_MAX routes small batches to pai_coop.cuh)."""
+    monkeypatch.setenv("PAI_COOP_MAX", "0" if request.param.startswith("thread") else "1000000")
+
+
+odd_moduli = st.integers(min_value=3, max_value=2 ** 1100).map(lambda x: x | 1)
 
 
 @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
 @given(mod=odd_moduli, data=st.data())
-def test_seam_matches_python(pkg, sim, mod, data):
+def test_seam_matches_python(pkg, sim, kernel_family, mod, data):
     ctx = pkg.ModContext(mod, engine=sim)
     lim = 2 ** (32 * ctx.limbs)
     a = data.draw(st.lists(st.integers(min_value=0, max_value=lim - 1), min_size=1, max_size=3))
@@ -38,8 +44,8 @@ def test_seam_matches_python(pkg, sim, mod, data):
 
 
 @settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
-@given(bits=st.integers(min_value=10, max_value=200), seed=st.integers(min_value=0, max_value=2 ** 32), data=st.data())
-def test_paillier_ops_match_python(pkg, sim, bits, seed, data):
+@given(bits=st.integers(min_value=10, max_value=600), seed=st.integers(min_value=0, max_value=2 ** 32), data=st.data())
+def test_paillier_ops_match_python(pkg, sim, kernel_family, bits, seed, data):
     import importlib
     import random
     util = importlib.import_module("python-paillier_b200.util")
