@@ -66,3 +66,21 @@ def test_shard_range(pkg):
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_build_tracks_every_device_header():
+    """A header missing from the staleness lists means an edited kernel silently keeps running from an old .so."""
+    import importlib
+    import os
+    import re
+    import __graft_entry__ as ge
+    build = importlib.import_module("python-paillier_b200.build")
+    csrc = build.CSRC
+    included = set()
+    for name in os.listdir(csrc):
+        with open(os.path.join(csrc, name)) as f:
+            included.update(re.findall(r'#include "(pai_[a-z_]+\.(?:cuh|h))"', f.read()))
+    assert included and included <= set(build.HEADERS)
+    with open(ge.__file__) as f:
+        text = f.read()
+    assert all('"%s"' % h in text for h in included)
