@@ -207,17 +207,22 @@ PAI_DEV void w_mont_mul(uint32_t (&r)[WL][K], const uint32_t (&a)[WL][K], const 
                         const uint32_t (&n)[WL][K], uint32_t n0inv) {
   uint64_t acc[WL][K];
   uint64_t sp[WL];                         // carry word at the position just above the lane's K limbs (small)
+  uint32_t pend[WL];                       // low word handed down by the lane above, one iteration late (K >= 2): the
+                                           // SHFL.DOWN then overlaps the next limb's products and quotient broadcast
+  uint32_t bj[WL], bsel[WL];
   PAI_EACH_LANE {
-    sp[ln] = 0;
+    sp[ln] = 0; pend[ln] = 0;
     PAI_UNROLL
     for (int k = 0; k < K; k++) acc[ln][k] = 0;
+    bsel[ln] = b[ln][0];
   }
+  w_bcast(bj, bsel, 0);
   for (int jt = 0; jt < 32; jt++) {
     PAI_UNROLL
     for (int jk = 0; jk < K; jk++) {
-      uint32_t bsel[WL], bj[WL], a0[WL], q[WL], low[WL], nl[WL];
-      PAI_EACH_LANE bsel[ln] = b[ln][jk];
-      w_bcast(bj, bsel, jt);
+      uint32_t bnext[WL], a0[WL], q[WL], low[WL], nl[WL];
+      PAI_EACH_LANE bsel[ln] = b[ln][(jk + 1) % K];
+      w_bcast(bnext, bsel, (jt + (jk + 1 == K ? 1 : 0)) & 31);       // multiplier limb of the next iteration
       PAI_EACH_LANE {
         PAI_UNROLL
         for (int k = 0; k < K; k++) acc[ln][k] += (uint64_t)a[ln][k] * bj[ln];
@@ -226,6 +231,7 @@ PAI_DEV void w_mont_mul(uint32_t (&r)[WL][K], const uint32_t (&a)[WL][K], const 
       w_bcast(q, a0, 0);
       PAI_EACH_LANE {
         const uint32_t qq = q[ln] * n0inv;
+        if (K >= 2) acc[ln][K - 1] += pend[ln];
         // high halves up one position (the top one into the lane's carry word), then the quotient row
         sp[ln] += acc[ln][K - 1] >> 32;
         PAI_UNROLL
@@ -240,15 +246,18 @@ PAI_DEV void w_mont_mul(uint32_t (&r)[WL][K], const uint32_t (&a)[WL][K], const 
       PAI_EACH_LANE {
         PAI_UNROLL
         for (int k = 0; k + 1 < K; k++) acc[ln][k] = (uint64_t)(uint32_t)acc[ln][k + 1] + (acc[ln][k] >> 32);
-        uint64_t v = (uint64_t)nl[ln] + (acc[ln][K - 1] >> 32) + sp[ln];
+        uint64_t v = (acc[ln][K - 1] >> 32) + sp[ln] + (K >= 2 ? 0u : nl[ln]);
         acc[ln][K - 1] = (uint32_t)v;
         sp[ln] = v >> 32;
+        pend[ln] = nl[ln];
+        bj[ln] = bnext[ln];
       }
     }
   }
   // positions are < 2^33: normalise inside the lane, then across lanes
   uint32_t out[WL][K];
   PAI_EACH_LANE {
+    if (K >= 2) acc[ln][K - 1] += pend[ln];
     uint64_t c = 0;
     PAI_UNROLL
     for (int k = 0; k < K; k++) { uint64_t t = acc[ln][k] + c; out[ln][k] = (uint32_t)t; c = t >> 32; }
