@@ -10,7 +10,9 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pkg = importlib.import_module("python-paillier_b200")
-from oracle.golden import H, load_golden  # noqa: E402  (fixture loader only: key material)
+import importlib
+_fx = importlib.import_module("python-paillier_b200.fixtures")
+H, load_golden = _fx.H, _fx.load_golden
 
 kb = int(os.environ.get("LAT_KEYBITS", 2048))
 fx = load_golden("vectors_%d.json" % kb)

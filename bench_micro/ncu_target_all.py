@@ -3,7 +3,9 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import paillier_b200 as pb
-from oracle.golden import H, load_golden
+import importlib
+_fx = importlib.import_module("python-paillier_b200.fixtures")
+H, load_golden = _fx.H, _fx.load_golden
 
 kb = 2048
 fx = load_golden("vectors_%d.json" % kb)

@@ -27,12 +27,16 @@ def main():
     ap.add_argument("--dim", type=int, default=100000)
     ap.add_argument("--clients", type=int, default=5)
     ap.add_argument("--key-bits", type=int, default=2048)
-    ap.add_argument("--cpu-sample", type=int, default=200, help="elements of the same round timed on one CPU core with the oracle port")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="measurement only: also time this many elements of the same round on one CPU core with the oracle port "
+                         "of the reference (oracle/, test infrastructure) and scale; 0 = GPU round only")
     args = ap.parse_args()
 
     import torch
     import paillier_b200 as phe
-    from oracle.golden import H, load_golden
+    import importlib
+    fixtures = importlib.import_module("python-paillier_b200.fixtures")
+    H, load_golden = fixtures.H, fixtures.load_golden
 
     fx = load_golden("vectors_%d.json" % args.key_bits)           # a fixed key keeps runs comparable
     pk = phe.PaillierPublicKey(H(fx["n"]))
