@@ -61,7 +61,14 @@ def _run(mod, skip=()):
     return res
 
 
-def test_reference_paillier_tests(aliased):
+@pytest.fixture(params=["thread-per-ciphertext", "warp-per-ciphertext"])
+def kernel_family(request, monkeypatch):
+    """The scalar phe API is a batch of one: on the GPU it runs on the warp-per-ciphertext kernels (pai_coop.cuh);
+    PAI_COOP_MAX=0 forces the throughput kernels.  The reference's tests must pass on both."""
+    monkeypatch.setenv("PAI_COOP_MAX", "0" if request.param.startswith("thread") else "1000000")
+
+
+def test_reference_paillier_tests(aliased, kernel_family):
     mod = _load(os.path.join(REF, "phe", "tests", "paillier_test.py"), "ref_paillier_test")
     # skipped: key-generation sweeps up to 4096 bits / 100 keys (out of the hot-path scope, hours in simulation)
     res = _run(mod, skip=("testKeyUniqueness", "testDefaultKeySize", "testStaticPrivateKeySize"))
@@ -69,7 +76,7 @@ def test_reference_paillier_tests(aliased):
     assert not res.failures and not res.errors, (res.failures[:2], res.errors[:2])
 
 
-def test_reference_util_and_math_tests(aliased):
+def test_reference_util_and_math_tests(aliased, kernel_family):
     mod = _load(os.path.join(REF, "phe", "tests", "util_test.py"), "ref_util_test")
     res = _run(mod, skip=("Fallbacks",))        # the fallback class toggles phe.util.HAVE_GMP / HAVE_CRYPTO internals
     assert res.testsRun >= 5 and not res.failures and not res.errors, (res.failures[:2], res.errors[:2])
