@@ -20,6 +20,11 @@
  *     so use one context per concurrently-used stream.
  *   - Every function returns 0 on success or a negative PAI_E_* code; pai_last_error() gives text.
  *   - There is NO CPU fallback: without a CUDA device every compute call fails with PAI_E_CUDA.
+ *   - Batch size needs no tuning: pai_encrypt / pai_decrypt / pai_mod_powmod_shared route a batch (or the remainder of
+ *     a batch beyond whole waves of the thread-per-ciphertext kernels) of up to 0.3 wave to warp-per-ciphertext
+ *     kernels with ~10x lower latency.  Environment switches, read at call time / context creation:
+ *     PAI_COOP_MAX=<rows> (0 = never use the warp kernels), PAI_ENCRYPT_PATH=full, PAI_DECRYPT_PATH=full (full-width
+ *     Montgomery kernels instead of the base-n digit kernels).  All variants return identical bits.
  */
 #ifndef PAILLIER_B200_H
 #define PAILLIER_B200_H
