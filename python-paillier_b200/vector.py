@@ -153,29 +153,34 @@ def decode_batch(public_key, limbs, exponents):
     exps = np.asarray(exponents, dtype=np.int64)
     small_pos = ~limbs[:, 2:].any(axis=1) if ln > 2 else np.ones(count, dtype=bool)
     low = limbs[:, 0].astype(np.uint64) | (limbs[:, 1].astype(np.uint64) << np.uint64(32)) if ln > 1 else limbs[:, 0].astype(np.uint64)
-    # n - enc for the candidates that are not small positives
+    # negatives are stored as n - |x| (phe/encoding.py:217-219): |x| = n - enc fits 64 bits exactly when the limbs above
+    # the low pair equal those of n (no borrow out of the low pair) or of n - 2^64 (borrow)
     nl = ints_to_limbs([n], ln)[0]
-    rest = np.nonzero(~small_pos)[0]
     neg_small = np.zeros(count, dtype=bool)
     neg_mag = np.zeros(count, dtype=np.uint64)
-    if len(rest):
-        rows = limbs[rest].astype(np.int64)
-        diff = np.zeros_like(rows)
-        borrow = np.zeros(len(rest), dtype=np.int64)
-        for j in range(ln):
-            d = np.int64(int(nl[j])) - rows[:, j] - borrow
-            borrow = (d < 0).astype(np.int64)
-            diff[:, j] = d + (borrow << 32)
-        ok = (borrow == 0) & ~(diff[:, 2:].any(axis=1) if ln > 2 else np.zeros(len(rest), dtype=bool))
+    rest = np.nonzero(~small_pos)[0]
+    if len(rest) and ln > 2 and n >> 64:
+        n_low = int(n & (2 ** 64 - 1))
+        hi0 = nl[2:]
+        hi1 = ints_to_limbs([(n >> 64) - 1], ln - 2)[0]
+        sub = limbs[rest]
+        lo = low[rest]
+        no_borrow = lo <= np.uint64(n_low)
+        same0 = (sub[:, 2:] == hi0).all(axis=1)
+        same1 = (sub[:, 2:] == hi1).all(axis=1)
+        ok = np.where(no_borrow, same0, same1)
         neg_small[rest] = ok
-        neg_mag[rest] = diff[:, 0].astype(np.uint64) | ((diff[:, 1].astype(np.uint64) << np.uint64(32)) if ln > 1 else np.uint64(0))
+        neg_mag[rest] = np.uint64(n_low) - lo              # modulo 2^64: the borrow is what `same1` accounts for
     fast = (small_pos | neg_small) & (exps < 0) & (exps > -250) & (public_key.max_int > 2 ** 64)
     if fast.any():
         mag = np.where(small_pos, low, neg_mag)
         val = np.ldexp(mag.astype(np.float64), (4 * exps).astype(np.int32)) if EncodedNumber.BASE == 16 else None
         val = np.where(small_pos, val, -val)
-        for i in np.nonzero(fast)[0]:
-            out[i] = float(val[i])
+        if fast.all():
+            out = val.tolist()
+        else:
+            for i, v in zip(np.nonzero(fast)[0].tolist(), val[fast].tolist()):
+                out[i] = v
     slow = np.nonzero(~fast)[0]
     if len(slow):
         encs = limbs_to_ints(limbs[slow])
