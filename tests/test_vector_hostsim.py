@@ -95,3 +95,35 @@ def test_vector_ops_match_scalar_semantics(pkg, env):
         va * vb
     with pytest.raises(ValueError):
         va + pk.encrypt_batch([1.0])
+
+
+def test_batched_codec_equals_scalar_codec(pkg):
+    """encode_batch / decode_batch (vectorised) against EncodedNumber.encode / decode element by element, including
+    magnitudes around 2^64 (the limit of the fast decode path), negatives that borrow across limbs, and values that
+    must take the exact slow path."""
+    import importlib
+    import random
+    import __graft_entry__ as ge
+    engine_mod = importlib.import_module("python-paillier_b200.engine")
+    vec = importlib.import_module("python-paillier_b200.vector")
+    engine_mod._set_engine_for_tests(pkg.Engine(ge.build_hostsim()))
+    try:
+        fx = load_golden("vectors_1024.json")
+        pk = pkg.PaillierPublicKey(H(fx["n"]))
+        rng = random.Random(11)
+        floats = [rng.uniform(-1, 1) * 10 ** rng.randrange(-30, 30) for _ in range(400)]
+        floats += [0.0, -0.0, 1.0, -1.0, 2.0 ** 63, -(2.0 ** 63), 2.0 ** 64, -(2.0 ** 64), 2.0 ** 64 * (1 + 2 ** -52), 1e-300, -1e300,
+                   float(2 ** 53 - 1), -float(2 ** 53 - 1), 5e-324]
+        limbs, exps = vec.encode_batch(pk, floats)
+        encs = [pkg.EncodedNumber.encode(pk, v) for v in floats]
+        assert pkg.limbs_to_ints(limbs) == [e.encoding for e in encs] and exps.tolist() == [e.exponent for e in encs]
+        assert vec.decode_batch(pk, limbs, exps) == [e.decode() for e in encs]
+        # encodings built directly: every combination of small / large magnitude, sign and exponent
+        n = pk.n
+        mags = [0, 1, 2 ** 32 - 1, 2 ** 32, 2 ** 64 - 1, 2 ** 64, 2 ** 64 + 1, (n & (2 ** 64 - 1)), (n & (2 ** 64 - 1)) + 1, 2 ** 200]
+        cases = [(m, e) for m in mags for e in (-1, -13, -60, -249, -250, 0, 3)] + [(n - m, e) for m in mags[1:] for e in (-1, -13, -60, 0)]
+        l2 = pkg.ints_to_limbs([c[0] for c in cases], limbs.shape[1])
+        e2 = [c[1] for c in cases]
+        assert vec.decode_batch(pk, l2, e2) == [pkg.EncodedNumber(pk, c[0], c[1]).decode() for c in cases]
+    finally:
+        engine_mod._set_engine_for_tests(None)
