@@ -190,6 +190,8 @@ def decode_batch(public_key, limbs, exponents):
 
 
 class EncryptedVector(object):
+    __array_ufunc__ = None          # numpy_array + vector / numpy_array * vector defer to __radd__ / __rmul__
+
     def __init__(self, public_key, limbs, exponents, obfuscated=False):
         self.public_key = public_key
         self.limbs = limbs                                  # torch.int32 [B, c_limbs] on the key's device
@@ -279,11 +281,11 @@ class EncryptedVector(object):
 
     # ------------------------------------------------------------------ arithmetic
     def _raw_mul_rows(self, limbs, scalars):
-        """limbs[i] ^ scalars[i] mod n^2 (device), scalars: list of ints in [0, n)."""
+        """limbs[i] ^ scalars[i] mod n^2 (device), scalars: list of ints in [0, n) or their limb matrix."""
         ctx = self.public_key.engine_context()
         torch = _torch()
         count = int(limbs.shape[0])
-        d_s = _to_dev(ints_to_limbs(scalars, ctx.n_limbs), ctx)
+        d_s = _to_dev(scalars if isinstance(scalars, np.ndarray) else ints_to_limbs(scalars, ctx.n_limbs), ctx)
         out = torch.empty_like(limbs)
         status = torch.zeros((count,), dtype=torch.int32, device=limbs.device)
         ctx.raw_mul_dev(limbs, d_s, out, status, count)
@@ -338,13 +340,22 @@ class EncryptedVector(object):
         scalars = list(other) if hasattr(other, "__len__") else [other] * len(self)
         if len(scalars) != len(self):
             raise ValueError("length mismatch")
-        encs = [s if isinstance(s, EncodedNumber) else EncodedNumber.encode(self.public_key, s, max_exponent=int(e))
-                for s, e in zip(scalars, self.exponents)]
-        new_exps = np.minimum(self.exponents, np.array([e.exponent for e in encs], dtype=np.int64))
-        a = self.decrease_exponent_to(new_exps)
-        encs = [e.decrease_exponent_to(int(x)) if e.exponent > x else e for e, x in zip(encs, new_exps)]
         n = self.public_key.n
-        nude = [(n * e.encoding + 1) % self.public_key.nsquare for e in encs]      # raw_encrypt(., r=1), phe/paillier.py:673
+        if any(isinstance(s, EncodedNumber) for s in scalars):
+            encs = [s if isinstance(s, EncodedNumber) else EncodedNumber.encode(self.public_key, s, max_exponent=int(e))
+                    for s, e in zip(scalars, self.exponents)]
+            new_exps = np.minimum(self.exponents, np.array([e.exponent for e in encs], dtype=np.int64))
+            a = self.decrease_exponent_to(new_exps)
+            encs = [e.decrease_exponent_to(int(x)) if e.exponent > x else e for e, x in zip(encs, new_exps)]
+            encodings = [e.encoding for e in encs]
+        else:
+            # plain numbers: one vectorised encode against every element's exponent; the encoded exponent never exceeds
+            # it (max_exponent), so only `self` may need aligning
+            s_limbs, new_exps = encode_batch(self.public_key, other if isinstance(other, np.ndarray) else scalars,
+                                             max_exponent=self.exponents)
+            a = self.decrease_exponent_to(new_exps)
+            encodings = limbs_to_ints(s_limbs)
+        nude = [(n * e + 1) % self.public_key.nsquare for e in encodings]          # raw_encrypt(., r=1), phe/paillier.py:673
         d_b = _to_dev(ints_to_limbs(nude, ctx.c_limbs), ctx)
         out = torch.empty_like(a.limbs)
         if len(self):
@@ -359,9 +370,14 @@ class EncryptedVector(object):
         scalars = list(other) if hasattr(other, "__len__") else [other] * len(self)
         if len(scalars) != len(self):
             raise ValueError("length mismatch")
-        encs = [s if isinstance(s, EncodedNumber) else EncodedNumber.encode(self.public_key, s) for s in scalars]
-        out = self._raw_mul_rows(self.limbs, [e.encoding for e in encs]) if len(self) else self.limbs
-        return EncryptedVector(self.public_key, out, self.exponents + np.array([e.exponent for e in encs], dtype=np.int64))
+        if any(isinstance(s, EncodedNumber) for s in scalars):
+            encs = [s if isinstance(s, EncodedNumber) else EncodedNumber.encode(self.public_key, s) for s in scalars]
+            s_limbs = ints_to_limbs([e.encoding for e in encs], self.public_key.engine_context().n_limbs)
+            s_exps = np.array([e.exponent for e in encs], dtype=np.int64)
+        else:
+            s_limbs, s_exps = encode_batch(self.public_key, other if isinstance(other, np.ndarray) else scalars)
+        out = self._raw_mul_rows(self.limbs, s_limbs) if len(self) else self.limbs
+        return EncryptedVector(self.public_key, out, self.exponents + s_exps)
 
     __rmul__ = __mul__
 

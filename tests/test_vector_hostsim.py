@@ -72,6 +72,16 @@ def test_vector_ops_match_scalar_semantics(pkg, env):
         assert vres.ciphertexts(False) == [x.ciphertext(False) for x in sres]
         assert vres.exponents.tolist() == [x.exponent for x in sres]
         assert sk.decrypt_batch(vres) == [sk.decrypt(x) for x in sres]
+    # all-float operands take the vectorised encode path (lists and numpy arrays): same bits as element by element
+    bf = [float(x) for x in b]
+    for operand in (bf, np.array(bf)):
+        for vres, sres in (((va + operand), [x + y for x, y in zip(sa, bf)]), ((va * operand), [x * y for x, y in zip(sa, bf)]),
+                           ((operand + va), [y + x for x, y in zip(sa, bf)])):
+            assert vres.ciphertexts(False) == [x.ciphertext(False) for x in sres]
+            assert vres.exponents.tolist() == [x.exponent for x in sres]
+    bi = [int(x * 100) for x in b]
+    assert (va * bi).ciphertexts(False) == [(x * y).ciphertext(False) for x, y in zip(sa, bi)]
+    assert (va + bi).ciphertexts(False) == [(x + y).ciphertext(False) for x, y in zip(sa, bi)]
     assert sk.decrypt((va + vb).sum()) == pytest.approx(sum(a) + sum(b), abs=1e-12)
     fresh = pk.encrypt_batch(a)
     c0 = fresh.ciphertexts(False)
