@@ -15,9 +15,12 @@
  *   - Pointers named d_* are DEVICE pointers (e.g. torch tensor.data_ptr()); the *_host variants take
  *     HOST pointers and stage H2D/D2H inside the call (pinned staging, synchronous on return).
  *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Device-pointer calls are
- *     asynchronous on that stream.  A context may be used from several host threads if each call
- *     uses its own stream... except that calls sharing a context serialise on its table workspace,
- *     so use one context per concurrently-used stream.
+ *     asynchronous on that stream.
+ *   - Threads and streams: every entry point that takes a context locks it for the duration of the call
+ *     (host-pointer variants: until their results are back in host memory), so one context may be shared by any
+ *     number of host threads.  Scratch memory (window tables, work counters, intermediate rows) is kept per
+ *     (context, stream): calls on different streams run concurrently on the device without sharing any of it;
+ *     each stream a context is used on costs one table workspace (about 0.5 GB at 2048-bit keys).
  *   - Every function returns 0 on success or a negative PAI_E_* code; pai_last_error() gives text.
  *   - There is NO CPU fallback: without a CUDA device every compute call fails with PAI_E_CUDA.
  *   - Batch size needs no tuning: pai_encrypt / pai_decrypt / pai_mod_powmod_shared route a batch (or the remainder of
@@ -75,6 +78,10 @@ int pai_pub_create(const uint32_t* n, int limbs, int device, pai_pub** out);
 int pai_pub_destroy(pai_pub* k);
 int pai_pub_n_limbs(const pai_pub* k);     /* Ln : limbs of plaintexts / r / scalars (multiple of 16) */
 int pai_pub_c_limbs(const pai_pub* k);     /* 2*Ln: limbs of ciphertexts                              */
+/* rows one full wave of the throughput encrypt kernel holds on this device (a batch that is a multiple of it wastes
+ * nothing; host code that pipelines a long vector in chunks sizes the chunks with it).  No reference counterpart:
+ * the reference processes one element per call (examples/federated_learning_with_encryption.py:122-133). */
+long pai_pub_wave(pai_pub* k);
 
 /* c[i] = (1 + n*m[i]) * r[i]^n mod n^2        raw_encrypt, phe/paillier.py:102-139
  * (= obfuscate of the nude ciphertext, :603-624).  Any m, r < 2^(32 Ln) is accepted and reduced. */
@@ -97,6 +104,7 @@ int pai_priv_create(const uint32_t* p, const uint32_t* q, int limbs, int device,
 int pai_priv_destroy(pai_priv* k);
 int pai_priv_n_limbs(const pai_priv* k);
 int pai_priv_c_limbs(const pai_priv* k);
+long pai_priv_wave(pai_priv* k);            /* as pai_pub_wave, for the decrypt kernel */
 /* copies of the derived constants (host buffers of pai_priv_n_limbs() limbs each; NULL = skip):
  * p, q (ordered), p_inverse, hp, hq -- for the drop-in key object's attributes */
 int pai_priv_get(const pai_priv* k, uint32_t* p, uint32_t* q, uint32_t* p_inverse, uint32_t* hp, uint32_t* hq);

@@ -10,6 +10,7 @@
 #include "pai_rt.h"
 
 #include <algorithm>
+#include <map>
 #include <mutex>
 #include <new>
 
@@ -284,10 +285,9 @@ struct DevBuf {
   void release() { rt_free(p); p = nullptr; bytes = 0; }
 };
 
-// work counters of the persistent kernels: a ring of zero-initialised 64-bit counters per context; each
-// launch takes the next one and re-zeroes it on the launch stream first (launches on one stream are
-// ordered, so a counter is never re-armed while a previous kernel still uses it unless > 64 launches
-// are in flight on different streams -- callers use one context per concurrently used stream).
+// work counters of the persistent kernels: a ring of zero-initialised 64-bit counters per (context, stream);
+// each launch takes the next one and re-zeroes it on the launch stream first (launches on one stream are
+// ordered, so a counter is never re-armed while a previous kernel on that stream still uses it).
 struct Counters {
   DevBuf buf; int next = 0;
   int take(rt_stream s, unsigned long long** out) {
@@ -300,6 +300,22 @@ struct Counters {
     return rc;
   }
 };
+
+// Everything a launch borrows from its context while it runs: the window-table workspace, the work counters and the
+// intermediate rows of multi-kernel operations.  One set per CUDA stream the context has been used on, so calls on
+// different streams never share scratch memory (launches on ONE stream are ordered and may).  Looked up under the
+// context's mutex; lives until the context is destroyed.
+struct StreamWs {
+  DevBuf tbl, w_base, w_exp, w_flag, coop_u, red_a, red_b;
+  Counters ctr;
+  void release() { tbl.release(); w_base.release(); w_exp.release(); w_flag.release(); coop_u.release(); red_a.release(); red_b.release(); ctr.buf.release(); }
+};
+struct WsMap {
+  std::map<rt_stream, StreamWs> m;
+  StreamWs& get(rt_stream s) { return m[s]; }
+  void release() { for (auto& kv : m) kv.second.release(); m.clear(); }
+};
+typedef std::lock_guard<std::recursive_mutex> CtxLock;
 
 // launch geometry for a body with `nbuf` operand buffers of NT tiles
 struct Geom { int nthr, grid; size_t smem; };
@@ -330,8 +346,10 @@ struct pai_mod {
   int device = 0, NT = 0, L = 0;
   uint32_t* d_blob = nullptr;       // mc_limbs(NT) (+ extra room requested by the owner)
   limbs_t h_N;                      // padded modulus
-  DevBuf tbl, tmp_a, tmp_b, tmp_o, tmp_s, tmp_e;
-  Counters ctr;
+  DevBuf tmp_a, tmp_b, tmp_o, tmp_s, tmp_e;   // staging of the host-pointer entry points (used under `mu`, stream 0)
+  WsMap ws;                         // per-stream workspaces
+  std::recursive_mutex mu;          // serialises host threads on this context (recursive: coop constants are built
+                                    // through the context's own entry points)
   // warp-per-ciphertext layout (pai_coop.cuh), built on first use: [ N | R^2 mod N | R^3 mod N ], R = 2^(32*32*coopK)
   uint32_t* d_coop = nullptr; int coopK = 0; uint32_t coop_n0inv = 0; bool coop_building = false;
 };
@@ -339,7 +357,9 @@ struct pai_pub {
   pai_mod* nsq = nullptr;           // modulus n^2; its blob is followed by n (4*NT limbs) for encrypt
   int ln = 0;                       // limbs of n (= 4*NT)
   uint32_t* d_nth = nullptr;        // [ n | n - max_int ]  (ln limbs each) for raw_mul's branch test
-  DevBuf w_base, w_exp, w_flag, h_m, h_r, h_c, h_s;
+  DevBuf h_m, h_r, h_c, h_s;        // staging of the host-pointer entry points (under `mu`)
+  WsMap ws;                         // per-stream intermediates of raw_mul / reductions
+  std::recursive_mutex mu;
   limbs_t h_n;
   uint32_t* d_prog = nullptr;       // sliding-window program of the exponent n (encrypt)
   int nops = 0, nodd = 0;
@@ -357,11 +377,11 @@ struct pai_priv {
   bool use_digit = true;
   int nwin_p = 0, nwin_q = 0;
   limbs_t h_p, h_q, h_pinv, h_hp, h_hq;   // 16*NTP limbs each (padded)
-  DevBuf tbl, h_c, h_m;
-  Counters ctr;
+  DevBuf h_c, h_m;                  // staging of pai_decrypt_host (under `mu`)
+  WsMap ws;                         // per-stream window tables, counters, warp-path intermediates
+  std::recursive_mutex mu;
   long wave = 0;                    // ciphertexts per wave of the throughput decrypt kernel (lazily measured)
   uint32_t* d_coop_e = nullptr;     // [ p - 1 | q - 1 ] (8*NTP limbs each) for the warp-per-ciphertext path
-  DevBuf coop_u;                    // its two half results per ciphertext
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -453,7 +473,7 @@ void mod_free(pai_mod* m) {
   rt_set_device(m->device);
   rt_free(m->d_blob);
   if (m->d_coop) { rt_memset(m->d_coop, 0, (size_t)3 * 32 * m->coopK * 4, 0); rt_sync(0); rt_free(m->d_coop); }
-  m->ctr.buf.release(); m->tbl.release(); m->tmp_a.release(); m->tmp_b.release(); m->tmp_o.release(); m->tmp_s.release(); m->tmp_e.release();
+  m->ws.release(); m->tmp_a.release(); m->tmp_b.release(); m->tmp_o.release(); m->tmp_s.release(); m->tmp_e.release();
   delete m;
 }
 
@@ -475,12 +495,12 @@ int do_powmod(pai_mod* m, const uint32_t* base, int base_tiles, const uint32_t* 
   int cq = mc_limbs(NT) / 4;
   int rc = geometry<B>(m->device, NT, cq, 3, batch, g);
   if (rc) return rc;
-  rc = m->tbl.ensure(table_bytes(g, NT, W_VAR));
+  rc = m->ws.get(s).tbl.ensure(table_bytes(g, NT, W_VAR));
   if (rc) return rc;
   unsigned long long* ctr = nullptr;
-  rc = m->ctr.take(s, &ctr);
+  rc = m->ws.get(s).ctr.take(s, &ctr);
   if (rc) return rc;
-  B body{m->d_blob, cq, base, base_tiles, d_exp, exp_limbs, exp_stride, nwin_fixed, out, batch, (u4*)m->tbl.p, ctr};
+  B body{m->d_blob, cq, base, base_tiles, d_exp, exp_limbs, exp_stride, nwin_fixed, out, batch, (u4*)m->ws.get(s).tbl.p, ctr};
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
 }
 
@@ -503,12 +523,12 @@ int do_encrypt(pai_pub* k, const uint32_t* m_, const uint32_t* r, uint32_t* c, l
   int cq = mc_limbs(NT) / 4 + NT;
   int rc = geometry<B>(m->device, NT, cq, 2, batch, g);
   if (rc) return rc;
-  rc = m->tbl.ensure((size_t)g.grid * (size_t)(k->nodd + 1) * 2 * NT * g.nthr * 16);
+  rc = m->ws.get(s).tbl.ensure((size_t)g.grid * (size_t)(k->nodd + 1) * 2 * NT * g.nthr * 16);
   if (rc) return rc;
   unsigned long long* ctr = nullptr;
-  rc = m->ctr.take(s, &ctr);
+  rc = m->ws.get(s).ctr.take(s, &ctr);
   if (rc) return rc;
-  B body{m->d_blob, cq, k->d_prog, k->nops, k->nodd, m_, r, c, batch, (u4*)m->tbl.p, ctr};
+  B body{m->d_blob, cq, k->d_prog, k->nops, k->nodd, m_, r, c, batch, (u4*)m->ws.get(s).tbl.p, ctr};
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
 }
 
@@ -532,12 +552,12 @@ int do_encrypt_digit(pai_pub* k, const uint32_t* m_, const uint32_t* r, uint32_t
   int cq = dc_enc_limbs(NTH) / 4;
   int rc = geometry<B>(m->device, 2 * NTH, cq, 2, batch, g);
   if (rc) return rc;
-  rc = m->tbl.ensure((size_t)g.grid * (size_t)(k->nodd + 1) * 4 * NTH * g.nthr * 16);
+  rc = m->ws.get(s).tbl.ensure((size_t)g.grid * (size_t)(k->nodd + 1) * 4 * NTH * g.nthr * 16);
   if (rc) return rc;
   unsigned long long* ctr = nullptr;
-  rc = m->ctr.take(s, &ctr);
+  rc = m->ws.get(s).ctr.take(s, &ctr);
   if (rc) return rc;
-  B body{k->d_enc_consts, cq, k->d_prog, k->nops, k->nodd, m_, r, c, batch, (u4*)m->tbl.p, ctr, m->d_blob + dc_zero_offset(NTH)};
+  B body{k->d_enc_consts, cq, k->d_prog, k->nops, k->nodd, m_, r, c, batch, (u4*)m->ws.get(s).tbl.p, ctr, m->d_blob + dc_zero_offset(NTH)};
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
 }
 
@@ -558,12 +578,12 @@ int do_powmod_digit(pai_pub* k, const uint32_t* base, const uint32_t* d_exp, int
   int cq = dc_pow_limbs(NTH) / 4;
   int rc = geometry<B>(m->device, 2 * NTH, cq, 2, batch, g);
   if (rc) return rc;
-  rc = m->tbl.ensure((size_t)g.grid * ((size_t)1 << W_VAR) * 4 * NTH * g.nthr * 16);
+  rc = m->ws.get(s).tbl.ensure((size_t)g.grid * ((size_t)1 << W_VAR) * 4 * NTH * g.nthr * 16);
   if (rc) return rc;
   unsigned long long* ctr = nullptr;
-  rc = m->ctr.take(s, &ctr);
+  rc = m->ws.get(s).ctr.take(s, &ctr);
   if (rc) return rc;
-  B body{k->d_enc_consts, cq, base, d_exp, exp_limbs, out, batch, (u4*)m->tbl.p, ctr, m->d_blob + dc_zero_offset(NTH)};
+  B body{k->d_enc_consts, cq, base, d_exp, exp_limbs, out, batch, (u4*)m->ws.get(s).tbl.p, ctr, m->d_blob + dc_zero_offset(NTH)};
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
 }
 
@@ -575,12 +595,12 @@ int do_decrypt(pai_priv* k, const uint32_t* c, uint32_t* out, long batch, rt_str
   int cq = 2 * (mc_limbs(2 * NTP) / 4 + mc_limbs(NTP) / 4 + 6 * NTP) + 2 * NTP;
   int rc = geometry<B>(k->device, 2 * NTP, cq, 3, batch, g);
   if (rc) return rc;
-  rc = k->tbl.ensure(table_bytes(g, 2 * NTP, W_DEC));
+  rc = k->ws.get(s).tbl.ensure(table_bytes(g, 2 * NTP, W_DEC));
   if (rc) return rc;
   unsigned long long* ctr = nullptr;
-  rc = k->ctr.take(s, &ctr);
+  rc = k->ws.get(s).ctr.take(s, &ctr);
   if (rc) return rc;
-  B body{k->d_consts, cq, k->nwin_p, k->nwin_q, c, out, batch, (u4*)k->tbl.p, ctr, pre_p, pre_q};
+  B body{k->d_consts, cq, k->nwin_p, k->nwin_q, c, out, batch, (u4*)k->ws.get(s).tbl.p, ctr, pre_p, pre_q};
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
 }
 
@@ -591,12 +611,12 @@ int do_decrypt_digit(pai_priv* k, const uint32_t* c, uint32_t* out, long batch, 
   int cq = 2 * (dside_limbs<NTP>() / 4) + 2 * NTP;
   int rc = geometry<B>(k->device, 2 * NTP, cq, 2, batch, g);
   if (rc) return rc;
-  rc = k->tbl.ensure((size_t)g.grid * ((size_t)1 << W_DEC) * 4 * NTP * g.nthr * 16);
+  rc = k->ws.get(s).tbl.ensure((size_t)g.grid * ((size_t)1 << W_DEC) * 4 * NTP * g.nthr * 16);
   if (rc) return rc;
   unsigned long long* ctr = nullptr;
-  rc = k->ctr.take(s, &ctr);
+  rc = k->ws.get(s).ctr.take(s, &ctr);
   if (rc) return rc;
-  B body{k->d_dconsts, cq, k->nwin_p, k->nwin_q, c, out, batch, (u4*)k->tbl.p, ctr};
+  B body{k->d_dconsts, cq, k->nwin_p, k->nwin_q, c, out, batch, (u4*)k->ws.get(s).tbl.p, ctr};
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
 }
 
@@ -669,8 +689,8 @@ int do_side(pai_priv* k, pai_mod* m2, pai_mod* m1, const limbs_t& x, const limbs
     int cq = mc_limbs(NT2) / 4 + mc_limbs(NTP) / 4 + 6 * NTP;
     Geom g;
     rc = geometry<B>(k->device, NT2, cq, 3, 1, g);
-    if (!rc) rc = k->tbl.ensure(table_bytes(g, NT2, W_DEC));
-    if (!rc) { B body{d_side, cq, nwin, (const uint32_t*)d_g, (uint32_t*)d_l, (u4*)k->tbl.p}; rc = rt_launch(body, 1, g.nthr, g.smem, s); }
+    if (!rc) rc = k->ws.get(s).tbl.ensure(table_bytes(g, NT2, W_DEC));
+    if (!rc) { B body{d_side, cq, nwin, (const uint32_t*)d_g, (uint32_t*)d_l, (u4*)k->ws.get(s).tbl.p}; rc = rt_launch(body, 1, g.nthr, g.smem, s); }
   }
   // h = l^-1 mod x  (phe/paillier.py:360), then hM = h * R mod x
   if (!rc) rc = do_invert<NTP>(m1, (const uint32_t*)d_l, NTP, nullptr, (uint32_t*)d_h, (int32_t*)d_st, 1, s);
@@ -830,6 +850,28 @@ static int do_coop_decrypt_pow(pai_priv* k, const uint32_t* d_c, uint32_t* up, u
   return rt_launch_coop(b, grid, 32 * COOP_WARPS, smem, s);
 }
 
+// rows per full wave of the throughput kernels (measured once per context from the launch geometry)
+static int pub_wave(pai_pub* k) {
+  int rc = 0;
+  if (!k->wave) {
+    if (k->use_digit) { DISPATCH_NTH(k->nmod->NT, k->wave = encrypt_wave_digit<NTH>(k)); }
+    else { DISPATCH_NT(k->nsq->NT, k->wave = (wave_of<EncBody<NT>>(k->nsq->device, NT, mc_limbs(NT) / 4 + NT, 2))); }
+    if (rc) return rc;
+    if (k->wave <= 0) k->wave = 1;
+  }
+  return 0;
+}
+static int priv_wave(pai_priv* k) {
+  int rc = 0;
+  if (!k->wave) {
+    if (k->use_digit) { DISPATCH_NTP(k->NTP, k->wave = (wave_of<DecDigitBody<NTP, W_DEC>>(k->device, 2 * NTP, 2 * (dside_limbs<NTP>() / 4) + 2 * NTP, 2))); }
+    else { DISPATCH_NTP(k->NTP, k->wave = (wave_of<DecBody<NTP, W_DEC>>(k->device, 2 * NTP, 2 * (mc_limbs(2 * NTP) / 4 + mc_limbs(NTP) / 4 + 6 * NTP) + 2 * NTP, 3))); }
+    if (rc) return rc;
+    if (k->wave <= 0) k->wave = 1;
+  }
+  return 0;
+}
+
 extern "C" {
 
 const char* pai_last_error(void) { return g_err.c_str(); }
@@ -847,6 +889,7 @@ int pai_mod_limbs(const pai_mod* m) { return m ? m->L : PAI_E_ARG; }
 int pai_mod_mulmod(pai_mod* m, const uint32_t* d_a, const uint32_t* d_b, uint32_t* d_out, long batch, void* stream) {
   DeviceGuard device_guard_; (void)device_guard_;
   if (!m || !d_a || !d_b || !d_out || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  CtxLock lock_(m->mu);
   if (batch == 0) return 0;
   int rc = rt_set_device(m->device);
   if (rc) return rc;
@@ -866,6 +909,7 @@ int pai_mod_powmod_shared(pai_mod* m, const uint32_t* d_base, int base_limbs, co
                           uint32_t* d_out, long batch, void* stream) {
   DeviceGuard device_guard_; (void)device_guard_;
   if (!m || !d_base || !exponent || !d_out || batch < 0 || exp_limbs <= 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  CtxLock lock_(m->mu);
   if (batch == 0) return 0;
   int rc = rt_set_device(m->device);
   if (rc) return rc;
@@ -893,6 +937,7 @@ int pai_mod_powmod(pai_mod* m, const uint32_t* d_base, int base_limbs, const uin
                    uint32_t* d_out, long batch, void* stream) {
   DeviceGuard device_guard_; (void)device_guard_;
   if (!m || !d_base || !d_exp || !d_out || batch < 0 || exp_limbs <= 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  CtxLock lock_(m->mu);
   if (batch == 0) return 0;
   int rc = rt_set_device(m->device);
   if (rc) return rc;
@@ -902,6 +947,7 @@ int pai_mod_powmod(pai_mod* m, const uint32_t* d_base, int base_limbs, const uin
 int pai_mod_invert(pai_mod* m, const uint32_t* d_a, int a_limbs, uint32_t* d_out, int32_t* d_status, long batch, void* stream) {
   DeviceGuard device_guard_; (void)device_guard_;
   if (!m || !d_a || !d_out || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  CtxLock lock_(m->mu);
   if (a_limbs != m->L) { g_err = "a_limbs must equal pai_mod_limbs()"; return PAI_E_ARG; }
   if (batch == 0) return 0;
   int rc = rt_set_device(m->device);
@@ -969,7 +1015,7 @@ int pai_pub_destroy(pai_pub* k) {
   rt_free(k->d_nth);
   rt_free(k->d_prog);
   rt_free(k->d_enc_consts);
-  k->w_base.release(); k->w_exp.release(); k->w_flag.release(); k->h_m.release(); k->h_r.release(); k->h_c.release(); k->h_s.release();
+  k->ws.release(); k->h_m.release(); k->h_r.release(); k->h_c.release(); k->h_s.release();
   mod_free(k->nsq);
   mod_free(k->nmod);
   delete k;
@@ -977,19 +1023,23 @@ int pai_pub_destroy(pai_pub* k) {
 }
 int pai_pub_n_limbs(const pai_pub* k) { return k ? k->ln : PAI_E_ARG; }
 int pai_pub_c_limbs(const pai_pub* k) { return k ? 2 * k->ln : PAI_E_ARG; }
+long pai_pub_wave(pai_pub* k) {
+  DeviceGuard device_guard_; (void)device_guard_;
+  if (!k) return PAI_E_ARG;
+  CtxLock lock_(k->mu);
+  if (rt_set_device(k->nsq->device) || pub_wave(k)) return PAI_E_CUDA;
+  return k->wave;
+}
 
 int pai_encrypt(pai_pub* k, const uint32_t* d_m, const uint32_t* d_r, uint32_t* d_c, long batch, void* stream) {
   DeviceGuard device_guard_; (void)device_guard_;
   if (!k || !d_m || !d_r || !d_c || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  CtxLock lock_(k->mu);
   if (batch == 0) return 0;
   int rc = rt_set_device(k->nsq->device);
   if (rc) return rc;
-  if (!k->wave) {
-    if (k->use_digit) { DISPATCH_NTH(k->nmod->NT, k->wave = encrypt_wave_digit<NTH>(k)); }
-    else { DISPATCH_NT(k->nsq->NT, k->wave = (wave_of<EncBody<NT>>(k->nsq->device, NT, mc_limbs(NT) / 4 + NT, 2))); }
-    if (rc) return rc;
-    if (k->wave <= 0) k->wave = 1;
-  }
+  rc = pub_wave(k);
+  if (rc) return rc;
   const long ncoop = coop_rows(batch, k->wave);     // small batch / tail: one warp per ciphertext (pai_coop.cuh)
   if (ncoop) {
     pai_mod* m = k->nsq;
@@ -1062,33 +1112,35 @@ int pai_raw_add(pai_pub* k, const uint32_t* d_a, const uint32_t* d_b, uint32_t* 
 int pai_raw_mul(pai_pub* k, const uint32_t* d_a, const uint32_t* d_s, uint32_t* d_c, int32_t* d_status, long batch, void* stream) {
   DeviceGuard device_guard_; (void)device_guard_;
   if (!k || !d_a || !d_s || !d_c || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  CtxLock lock_(k->mu);
   if (batch == 0) return 0;
   pai_mod* m = k->nsq;
   rt_stream s = (rt_stream)stream;
   int rc = rt_set_device(m->device);
   const int ln = k->ln, lc = 2 * k->ln;
-  if (!rc) rc = k->w_exp.ensure((size_t)batch * ln * 4);
-  if (!rc) rc = k->w_base.ensure((size_t)batch * lc * 4);
-  if (!rc) rc = k->w_flag.ensure((size_t)batch * 4 * 2);
+  StreamWs& w = k->ws.get(s);
+  if (!rc) rc = w.w_exp.ensure((size_t)batch * ln * 4);
+  if (!rc) rc = w.w_base.ensure((size_t)batch * lc * 4);
+  if (!rc) rc = w.w_flag.ensure((size_t)batch * 4 * 2);
   if (rc) return rc;
-  int32_t* flag = (int32_t*)k->w_flag.p;
+  int32_t* flag = (int32_t*)w.w_flag.p;
   int32_t* status = d_status ? d_status : flag + batch;
   // 1. branch test + exponent (s or n - s)
   {
-    PrepBody b{nullptr, 0, k->d_nth, k->d_nth + ln, ln, d_s, (uint32_t*)k->w_exp.p, flag, batch};
+    PrepBody b{nullptr, 0, k->d_nth, k->d_nth + ln, ln, d_s, (uint32_t*)w.w_exp.p, flag, batch};
     long blocks = (batch + 127) / 128;
     rc = rt_launch(b, (int)std::min(blocks, 65535L), 128, 0, s);
     if (rc) return rc;
   }
   // 2. base = a, or invert(a, n^2) where flagged
-  DISPATCH_NT(m->NT, rc = do_invert<NT>(m, d_a, lc / 8, flag, (uint32_t*)k->w_base.p, status, batch, s));
+  DISPATCH_NT(m->NT, rc = do_invert<NT>(m, d_a, lc / 8, flag, (uint32_t*)w.w_base.p, status, batch, s));
   if (rc) return rc;
   // 3. base ^ exponent mod n^2
   if (k->use_digit) {
-    DISPATCH_NTH(k->nmod->NT, rc = do_powmod_digit<NTH>(k, (const uint32_t*)k->w_base.p, (const uint32_t*)k->w_exp.p, ln, d_c, batch, s));
+    DISPATCH_NTH(k->nmod->NT, rc = do_powmod_digit<NTH>(k, (const uint32_t*)w.w_base.p, (const uint32_t*)w.w_exp.p, ln, d_c, batch, s));
     return rc;
   }
-  return powmod_common(m, (const uint32_t*)k->w_base.p, lc, (const uint32_t*)k->w_exp.p, ln, ln, -1, d_c, batch, stream);
+  return powmod_common(m, (const uint32_t*)w.w_base.p, lc, (const uint32_t*)w.w_exp.p, ln, ln, -1, d_c, batch, stream);
 }
 
 // ---------------------------------------------------------------------------------------- private key
@@ -1135,9 +1187,8 @@ int pai_priv_destroy(pai_priv* k) {
   }
   rt_free(k->d_dconsts);
   if (k->d_coop_e) { rt_memset(k->d_coop_e, 0, (size_t)16 * k->NTP * 4, 0); rt_sync(0); rt_free(k->d_coop_e); }
-  k->coop_u.release();
   mod_free(k->pd); mod_free(k->qd);
-  k->ctr.buf.release(); k->tbl.release(); k->h_c.release(); k->h_m.release();
+  k->ws.release(); k->h_c.release(); k->h_m.release();
   mod_free(k->p2); mod_free(k->q2); mod_free(k->p1); mod_free(k->q1);
   std::fill(k->h_p.begin(), k->h_p.end(), 0); std::fill(k->h_q.begin(), k->h_q.end(), 0);
   delete k;
@@ -1145,6 +1196,13 @@ int pai_priv_destroy(pai_priv* k) {
 }
 int pai_priv_n_limbs(const pai_priv* k) { return k ? 16 * k->NTP : PAI_E_ARG; }
 int pai_priv_c_limbs(const pai_priv* k) { return k ? 32 * k->NTP : PAI_E_ARG; }
+long pai_priv_wave(pai_priv* k) {
+  DeviceGuard device_guard_; (void)device_guard_;
+  if (!k) return PAI_E_ARG;
+  CtxLock lock_(k->mu);
+  if (rt_set_device(k->device) || priv_wave(k)) return PAI_E_CUDA;
+  return k->wave;
+}
 int pai_priv_get(const pai_priv* k, uint32_t* p, uint32_t* q, uint32_t* p_inverse, uint32_t* hp, uint32_t* hq) {
   if (!k) return PAI_E_ARG;
   const int ln = 16 * k->NTP, L1 = 8 * k->NTP;
@@ -1160,15 +1218,12 @@ int pai_priv_get(const pai_priv* k, uint32_t* p, uint32_t* q, uint32_t* p_invers
 int pai_decrypt(pai_priv* k, const uint32_t* d_c, uint32_t* d_m, long batch, void* stream) {
   DeviceGuard device_guard_; (void)device_guard_;
   if (!k || !d_c || !d_m || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  CtxLock lock_(k->mu);
   if (batch == 0) return 0;
   int rc = rt_set_device(k->device);
   if (rc) return rc;
-  if (!k->wave) {
-    if (k->use_digit) { DISPATCH_NTP(k->NTP, k->wave = (wave_of<DecDigitBody<NTP, W_DEC>>(k->device, 2 * NTP, 2 * (dside_limbs<NTP>() / 4) + 2 * NTP, 2))); }
-    else { DISPATCH_NTP(k->NTP, k->wave = (wave_of<DecBody<NTP, W_DEC>>(k->device, 2 * NTP, 2 * (mc_limbs(2 * NTP) / 4 + mc_limbs(NTP) / 4 + 6 * NTP) + 2 * NTP, 3))); }
-    if (rc) return rc;
-    if (k->wave <= 0) k->wave = 1;
-  }
+  rc = priv_wave(k);
+  if (rc) return rc;
   const long ncoop = coop_rows(batch, k->wave);
   if (ncoop) {
     // both big exponentiations on one warp each (pai_coop.cuh), then L, h and the CRT in the thread-per-ciphertext form
@@ -1185,9 +1240,10 @@ int pai_decrypt(pai_priv* k, const uint32_t* d_c, uint32_t* d_m, long batch, voi
       if (!rc) rc = rt_h2d(k->d_coop_e, e.data(), (size_t)2 * L1 * 4, s);
       if (!rc) rc = rt_sync(s);
     }
-    if (!rc) rc = k->coop_u.ensure((size_t)2 * ncoop * L2 * 4);
+    StreamWs& w = k->ws.get(s);
+    if (!rc) rc = w.coop_u.ensure((size_t)2 * ncoop * L2 * 4);
     if (rc) return rc;
-    uint32_t* up = (uint32_t*)k->coop_u.p;
+    uint32_t* up = (uint32_t*)w.coop_u.p;
     uint32_t* uq = up + (size_t)ncoop * L2;
     DISPATCH_K(k->p2->coopK, rc = do_coop_decrypt_pow<K>(k, d_c + off * 2 * L2, up, uq, ncoop, s));
     if (rc) return rc;
@@ -1206,6 +1262,7 @@ int pai_decrypt(pai_priv* k, const uint32_t* d_c, uint32_t* d_m, long batch, voi
 int pai_encrypt_host(pai_pub* k, const uint32_t* m, const uint32_t* r, uint32_t* c, long batch) {
   DeviceGuard device_guard_; (void)device_guard_;
   if (!k || !m || !r || !c || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  CtxLock lock_(k->mu);
   if (batch == 0) return 0;
   int rc = rt_set_device(k->nsq->device);
   if (rc) return rc;
@@ -1221,6 +1278,7 @@ int pai_encrypt_host(pai_pub* k, const uint32_t* m, const uint32_t* r, uint32_t*
 int pai_raw_add_host(pai_pub* k, const uint32_t* a, const uint32_t* b, uint32_t* c, long batch) {
   DeviceGuard device_guard_; (void)device_guard_;
   if (!k || !a || !b || !c || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  CtxLock lock_(k->mu);
   if (batch == 0) return 0;
   int rc = rt_set_device(k->nsq->device);
   if (rc) return rc;
@@ -1236,6 +1294,7 @@ int pai_raw_add_host(pai_pub* k, const uint32_t* a, const uint32_t* b, uint32_t*
 int pai_raw_mul_host(pai_pub* k, const uint32_t* a, const uint32_t* s, uint32_t* c, int32_t* status, long batch) {
   DeviceGuard device_guard_; (void)device_guard_;
   if (!k || !a || !s || !c || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  CtxLock lock_(k->mu);
   if (batch == 0) return 0;
   int rc = rt_set_device(k->nsq->device);
   if (rc) return rc;
@@ -1253,6 +1312,7 @@ int pai_raw_mul_host(pai_pub* k, const uint32_t* a, const uint32_t* s, uint32_t*
 int pai_decrypt_host(pai_priv* k, const uint32_t* c, uint32_t* m, long batch) {
   DeviceGuard device_guard_; (void)device_guard_;
   if (!k || !c || !m || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  CtxLock lock_(k->mu);
   if (batch == 0) return 0;
   int rc = rt_set_device(k->device);
   if (rc) return rc;
@@ -1267,6 +1327,7 @@ int pai_decrypt_host(pai_priv* k, const uint32_t* c, uint32_t* m, long batch) {
 int pai_mod_mulmod_host(pai_mod* m, const uint32_t* a, const uint32_t* b, uint32_t* out, long batch) {
   DeviceGuard device_guard_; (void)device_guard_;
   if (!m || !a || !b || !out || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  CtxLock lock_(m->mu);
   if (batch == 0) return 0;
   int rc = rt_set_device(m->device);
   if (rc) return rc;
@@ -1283,6 +1344,7 @@ int pai_mod_powmod_host(pai_mod* m, const uint32_t* base, int base_limbs, const 
                         uint32_t* out, long batch) {
   DeviceGuard device_guard_; (void)device_guard_;
   if (!m || !base || !exp || !out || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  CtxLock lock_(m->mu);
   if (batch == 0) return 0;
   int rc = rt_set_device(m->device);
   if (rc) return rc;
@@ -1302,6 +1364,7 @@ int pai_mod_powmod_host(pai_mod* m, const uint32_t* base, int base_limbs, const 
 int pai_mod_invert_host(pai_mod* m, const uint32_t* a, int a_limbs, uint32_t* out, int32_t* status, long batch) {
   DeviceGuard device_guard_; (void)device_guard_;
   if (!m || !a || !out || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
+  CtxLock lock_(m->mu);
   if (batch == 0) return 0;
   int rc = rt_set_device(m->device);
   if (rc) return rc;

@@ -86,13 +86,29 @@ class PaillierPublicKey(object):
 
     def raw_encrypt_batch(self, plaintexts, r_values=None):
         """Batched raw_encrypt: list of ints -> list of ints (one kernel launch)."""
+        plaintexts = list(plaintexts)
         for m in plaintexts:
             if not isinstance(m, int):
                 raise TypeError('Expected int type plaintext but got: %s' % type(m))
+        rnd = random.SystemRandom()
         if r_values is None:
-            rnd = random.SystemRandom()
             r_values = [rnd.randrange(1, self.n) for _ in plaintexts]
-        return self.engine_context().raw_encrypt(list(plaintexts), list(r_values))
+        else:
+            r_values = list(r_values)
+            if len(r_values) != len(plaintexts):
+                raise ValueError("plaintexts and r_values differ in length")
+        # per element exactly what raw_encrypt does with r (phe/paillier.py:136-137): a falsy r draws a fresh one,
+        # anything outside (0, n^2) is reduced as powmod would; the rare element whose r does not fit the engine's
+        # rows (n <= 2^(32 Ln) <= r < n^2, legal for the reference) takes the scalar path
+        lim = 1 << (32 * self.engine_context().n_limbs)
+        r_values = [(r or rnd.randrange(1, self.n)) for r in r_values]
+        r_values = [r if 0 < r < self.nsquare else r % self.nsquare for r in r_values]
+        wide = {i: self.raw_encrypt(plaintexts[i], r) for i, r in enumerate(r_values) if r >= lim}
+        if not wide:
+            return self.engine_context().raw_encrypt(plaintexts, r_values)
+        keep = [i for i in range(len(plaintexts)) if i not in wide]
+        bulk = iter(self.engine_context().raw_encrypt([plaintexts[i] for i in keep], [r_values[i] for i in keep]))
+        return [wide[i] if i in wide else next(bulk) for i in range(len(plaintexts))]
 
     def encrypt(self, value, precision=None, r_value=None):
         encoding = value if isinstance(value, EncodedNumber) else EncodedNumber.encode(self, value, precision)

@@ -10,6 +10,7 @@ Key generation helpers (out of the hot-path scope, phe/util.py:106-161, 381-443)
 """
 import math
 import random
+import threading
 from base64 import urlsafe_b64decode, urlsafe_b64encode
 from collections import OrderedDict
 
@@ -21,19 +22,23 @@ _USE_MULMOD_FROM_GMP_SIZE = (1 << 1000)
 _MAX_ENGINE_BITS = 8192
 
 _ctx_cache = OrderedDict()
+_ctx_lock = threading.Lock()
 _CTX_CACHE_SIZE = 16
 
 
 def _mod_ctx(modulus):
-    ctx = _ctx_cache.get(modulus)
-    if ctx is None:
-        ctx = _engine.ModContext(modulus)
-        _ctx_cache[modulus] = ctx
-        while len(_ctx_cache) > _CTX_CACHE_SIZE:
-            _ctx_cache.popitem(last=False)[1].close()
-    else:
-        _ctx_cache.move_to_end(modulus)
-    return ctx
+    """Least-recently-used cache of Montgomery contexts.  An evicted context is only dropped from the cache: another
+    thread may still be inside a call on it, so it is destroyed by its finaliser once the last reference is gone."""
+    with _ctx_lock:
+        ctx = _ctx_cache.get(modulus)
+        if ctx is None:
+            ctx = _engine.ModContext(modulus)
+            _ctx_cache[modulus] = ctx
+            while len(_ctx_cache) > _CTX_CACHE_SIZE:
+                _ctx_cache.popitem(last=False)
+        else:
+            _ctx_cache.move_to_end(modulus)
+        return ctx
 
 
 def _engine_modulus(c):

@@ -6,6 +6,7 @@ launch per vector operation, ciphertexts stay in HBM as [B, c_limbs] uint32 limb
 only converted to Python ints on request.  Semantics per element are those of EncryptedNumber
 (exponent alignment before add, phe/paillier.py:695-700; lazy obfuscation, :565-566).
 """
+import operator
 import os
 
 import numpy as np
@@ -31,6 +32,26 @@ def _to_host(t):
     return t.cpu().numpy().view(np.uint32)
 
 
+def _stream(ctx):
+    """The CUDA stream the engine kernels of this call are launched on: torch's CURRENT stream of the context's
+    device, so that they are ordered with the surrounding torch work (allocations, fills, index ops, .cpu()) also
+    inside ``with torch.cuda.stream(s)``.  The engine keeps its scratch memory per (context, stream)."""
+    if ctx.eng.simulated:
+        return None
+    return int(_torch().cuda.current_stream(ctx.device).cuda_stream)
+
+
+def _rows_for(ctx_limbs, t):
+    """Zero-pad (or trim all-zero columns of) a device limb matrix to `ctx_limbs` columns."""
+    have = int(t.shape[1])
+    if have == ctx_limbs:
+        return t
+    torch = _torch()
+    if have < ctx_limbs:
+        return torch.nn.functional.pad(t, (0, ctx_limbs - have)).contiguous()
+    return t[:, :ctx_limbs].contiguous()
+
+
 def limbs_to_decimal_strings(ctx, d_limbs):
     """Device limb matrix -> list of decimal strings (str(int) of every row), converted on the GPU."""
     torch = _torch()
@@ -39,7 +60,7 @@ def limbs_to_decimal_strings(ctx, d_limbs):
         return []
     width = decimal_width(limbs, ctx.eng)
     d_text = torch.empty((count, width), dtype=torch.uint8, device=d_limbs.device)
-    limbs_to_decimal_dev(d_limbs, limbs, d_text, count, ctx.device, engine=ctx.eng)
+    limbs_to_decimal_dev(d_limbs, limbs, d_text, count, ctx.device, stream=_stream(ctx), engine=ctx.eng)
     raw = d_text.cpu().numpy().tobytes()
     return [(raw[i * width:(i + 1) * width].lstrip(b"0") or b"0").decode("ascii") for i in range(count)]
 
@@ -57,7 +78,7 @@ def decimal_strings_to_limbs(ctx, strings, limbs):
     d_limbs = torch.empty((count, limbs), dtype=torch.int32, device=d_text.device)
     d_status = torch.zeros((count,), dtype=torch.int32, device=d_text.device)
     if count:
-        decimal_to_limbs_dev(d_text, width, d_limbs, limbs, d_status, count, ctx.device, engine=ctx.eng)
+        decimal_to_limbs_dev(d_text, width, d_limbs, limbs, d_status, count, ctx.device, stream=_stream(ctx), engine=ctx.eng)
         bad = torch.nonzero(d_status).flatten()
         if bad.numel():
             i = int(bad[0])
@@ -225,12 +246,12 @@ class EncryptedVector(object):
             # fresh obfuscators drawn on the device from a ChaCha20 stream keyed by os.urandom (pai_rng.cuh)
             d_r = torch.empty((count, ctx.n_limbs), dtype=torch.int32, device=d_m.device)
             if count:
-                ctx.random_lt_n_dev(d_r, count)
+                ctx.random_lt_n_dev(d_r, count, stream=_stream(ctx))
         else:
             d_r = _to_dev(ints_to_limbs(list(r_values), ctx.n_limbs), ctx)
         d_c = torch.empty((count, ctx.c_limbs), dtype=torch.int32, device=d_m.device)
         if count:
-            ctx.encrypt_dev(d_m, d_r, d_c, count)
+            ctx.encrypt_dev(d_m, d_r, d_c, count, stream=_stream(ctx))
         return cls(public_key, d_c, exponents, obfuscated=obf)
 
     @classmethod
@@ -260,8 +281,25 @@ class EncryptedVector(object):
         return out
 
     def __getitem__(self, i):
-        return self.to_encrypted_numbers()[i] if isinstance(i, int) else EncryptedVector(
-            self.public_key, self.limbs[i].contiguous(), self.exponents[i], self._obfuscated)
+        """v[int] -> EncryptedNumber (only that row leaves the device); v[slice / index array / mask] -> EncryptedVector."""
+        import numbers
+        if isinstance(i, numbers.Integral) and not isinstance(i, (bool, np.bool_)):
+            from .paillier import EncryptedNumber
+            k = operator.index(i)
+            if k < 0:
+                k += len(self)
+            if not 0 <= k < len(self):
+                raise IndexError("EncryptedVector index out of range")
+            x = EncryptedNumber(self.public_key, limbs_to_ints(_to_host(self.limbs[k:k + 1]))[0], int(self.exponents[k]))
+            if self._obfuscated:
+                x._mark_obfuscated()
+            return x
+        if isinstance(i, np.ndarray):
+            i = _torch().from_numpy(i).to(self.limbs.device)
+            exps = self.exponents[i.cpu().numpy()]
+        else:
+            exps = self.exponents[i]
+        return EncryptedVector(self.public_key, self.limbs[i].contiguous(), exps, self._obfuscated)
 
     def obfuscate(self):
         """c_i <- c_i * r_i^n mod n^2 with fresh r_i (phe/paillier.py:603-624): K1 with m = 0, then K3."""
@@ -270,12 +308,12 @@ class EncryptedVector(object):
         if count:
             torch = _torch()
             d_r = torch.empty((count, ctx.n_limbs), dtype=torch.int32, device=self.limbs.device)
-            ctx.random_lt_n_dev(d_r, count)
+            ctx.random_lt_n_dev(d_r, count, stream=_stream(ctx))
             d_zero = torch.zeros((count, ctx.n_limbs), dtype=torch.int32, device=self.limbs.device)
             d_rn = torch.empty_like(self.limbs)
-            ctx.encrypt_dev(d_zero, d_r, d_rn, count)
+            ctx.encrypt_dev(d_zero, d_r, d_rn, count, stream=_stream(ctx))
             out = torch.empty_like(self.limbs)
-            ctx.raw_add_dev(self.limbs, d_rn, out, count)
+            ctx.raw_add_dev(self.limbs, d_rn, out, count, stream=_stream(ctx))
             self.limbs = out
         self._obfuscated = True
 
@@ -288,7 +326,7 @@ class EncryptedVector(object):
         d_s = _to_dev(scalars if isinstance(scalars, np.ndarray) else ints_to_limbs(scalars, ctx.n_limbs), ctx)
         out = torch.empty_like(limbs)
         status = torch.zeros((count,), dtype=torch.int32, device=limbs.device)
-        ctx.raw_mul_dev(limbs, d_s, out, status, count)
+        ctx.raw_mul_dev(limbs, d_s, out, status, count, stream=_stream(ctx))
         if bool(status.any().item()):
             raise ZeroDivisionError('invert() no inverse exists')
         return out
@@ -317,7 +355,9 @@ class EncryptedVector(object):
             sub = limbs[tidx].contiguous()
             out = torch.empty_like(sub)
             status = torch.zeros((len(idx),), dtype=torch.int32, device=limbs.device)
-            ctx.raw_mul_dev(sub, _to_dev(scal, ctx), out, status, len(idx))
+            ctx.raw_mul_dev(sub, _to_dev(scal, ctx), out, status, len(idx), stream=_stream(ctx))
+            if bool(status.any().item()):
+                raise ZeroDivisionError('invert() no inverse exists')
             limbs = limbs.clone()
             limbs[tidx] = out
         return EncryptedVector(self.public_key, limbs, new_exps.copy(), obfuscated=self._obfuscated and not len(idx))
@@ -334,7 +374,7 @@ class EncryptedVector(object):
             a, b = self.decrease_exponent_to(new_exps), other.decrease_exponent_to(new_exps)
             out = torch.empty_like(a.limbs)
             if len(self):
-                ctx.raw_add_dev(a.limbs, b.limbs, out, len(self))
+                ctx.raw_add_dev(a.limbs, b.limbs, out, len(self), stream=_stream(ctx))
             return EncryptedVector(self.public_key, out, new_exps)
         # plaintext operand(s): encode against each element's exponent (phe/paillier.py:626-676)
         scalars = list(other) if hasattr(other, "__len__") else [other] * len(self)
@@ -359,7 +399,7 @@ class EncryptedVector(object):
         d_b = _to_dev(ints_to_limbs(nude, ctx.c_limbs), ctx)
         out = torch.empty_like(a.limbs)
         if len(self):
-            ctx.raw_add_dev(a.limbs, d_b, out, len(self))
+            ctx.raw_add_dev(a.limbs, d_b, out, len(self), stream=_stream(ctx))
         return EncryptedVector(self.public_key, out, new_exps)
 
     __radd__ = __add__
@@ -402,7 +442,7 @@ class EncryptedVector(object):
         while limbs.shape[0] > 1:
             half = limbs.shape[0] // 2
             out = torch.empty((half, limbs.shape[1]), dtype=torch.int32, device=limbs.device)
-            ctx.raw_add_dev(limbs[:half].contiguous(), limbs[half:2 * half].contiguous(), out, half)
+            ctx.raw_add_dev(limbs[:half].contiguous(), limbs[half:2 * half].contiguous(), out, half, stream=_stream(ctx))
             limbs = torch.cat([out, limbs[2 * half:]], dim=0) if limbs.shape[0] % 2 else out
         c = limbs_to_ints(_to_host(limbs))[0]
         return EncryptedNumber(self.public_key, c, int(v.exponents[0]))
@@ -446,10 +486,7 @@ class EncryptedVector(object):
         ctx = private_key.engine_context()
         torch = _torch()
         count = len(self)
-        d_m = torch.empty((count, ctx.n_limbs), dtype=torch.int32, device=self.limbs.device)
-        if count:
-            ctx.decrypt_dev(self.limbs, d_m, count)
-        plain = limbs_to_ints(_to_host(d_m))
+        plain = limbs_to_ints(self._decrypt_rows(ctx)) if count else []
         return [EncodedNumber(self.public_key, m, int(e)) for m, e in zip(plain, self.exponents)]
 
     def decrypt(self, private_key):
@@ -461,6 +498,14 @@ class EncryptedVector(object):
         count = len(self)
         if not count:
             return []
+        return decode_batch(self.public_key, self._decrypt_rows(ctx), self.exponents)
+
+    def _decrypt_rows(self, ctx):
+        """raw_decrypt of every row -> host uint32 matrix [B, n_limbs of the PUBLIC layout].  The private context sizes
+        its rows from max(p, q), the public one from n: for unbalanced primes they differ, and the rows are re-padded."""
+        torch = _torch()
+        count = len(self)
+        d_c = _rows_for(ctx.c_limbs, self.limbs)
         d_m = torch.empty((count, ctx.n_limbs), dtype=torch.int32, device=self.limbs.device)
-        ctx.decrypt_dev(self.limbs, d_m, count)
-        return decode_batch(self.public_key, _to_host(d_m), self.exponents)
+        ctx.decrypt_dev(d_c, d_m, count, stream=_stream(ctx))
+        return _to_host(_rows_for(self.public_key.engine_context().n_limbs, d_m))
