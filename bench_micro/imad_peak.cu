@@ -40,9 +40,9 @@ __global__ void k_wide_chain(uint32_t* out, const uint32_t* in, long long* cyc) 
 template <int OP, int NACC>
 __global__ void k_indep(uint32_t* out, const uint32_t* in, long long* cyc) {
   uint32_t a = in[threadIdx.x], b = in[threadIdx.x + 64];
-  uint32_t lo[NACC], hi[NACC];
+  uint32_t lo[NACC], hi[NACC], x[NACC], y[NACC];
   double d[NACC];
-  for (int i = 0; i < NACC; i++) { lo[i] = in[i]; hi[i] = in[i + 32]; d[i] = (double)in[i]; }
+  for (int i = 0; i < NACC; i++) { lo[i] = in[i]; hi[i] = in[i + 32]; d[i] = (double)in[i]; x[i] = in[i + 3]; y[i] = in[i + 5]; }
   double da = (double)a * 1e-9, db = (double)b * 1e-9;
   long long t0 = clock64();
 #pragma unroll 1
@@ -60,12 +60,21 @@ __global__ void k_indep(uint32_t* out, const uint32_t* in, long long* cyc) {
         if (OP == 4) asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+r"(lo[i]) : "r"(a & 31));
         if (OP == 5) asm volatile("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(lo[i]), "+r"(hi[i]) : "r"(a), "r"(b));
         if (OP == 6) asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;" : "+r"(lo[i]), "+r"(hi[i]) : "r"(lo[(i + 1) % NACC]), "r"(b));
+        // 7: the same multiplier WITHOUT a 64-bit addend (IMAD.WIDE.U32 Rd, Ra, Rb, RZ): separates the multiplier's rate from
+        //    the cost of reading the addend pair
+        if (OP == 7) { uint64_t v;
+                       asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(v) : "r"(lo[i]), "r"(b));
+                       lo[i] = (uint32_t)v ^ (uint32_t)(v >> 32); }
+        // 8: wide MAC pair + two independent ALU adds per MAC (do IADD3s issue in the shadow of the half-rate IMAD.WIDE?)
+        if (OP == 8) { asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;" : "+r"(lo[i]), "+r"(hi[i]) : "r"(lo[(i + 1) % NACC]), "r"(b));
+                       asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(a));
+                       asm volatile("add.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(b)); }
       }
     }
   }
   long long t1 = clock64();
   uint32_t s = 0;
-  for (int i = 0; i < NACC; i++) s ^= lo[i] ^ hi[i] ^ (uint32_t)d[i];
+  for (int i = 0; i < NACC; i++) s ^= lo[i] ^ hi[i] ^ (uint32_t)d[i] ^ x[i] ^ y[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
@@ -133,6 +142,8 @@ int main() {
     emit("imad_wide_nocarry", warps, run([&](uint32_t* o, const uint32_t* i, long long* c) { k_indep<2, 8><<<grid, block>>>(o, i, c); }, grid, block, 8.0 * 4 * ITERS, nsm));
     emit("imad_wide_pair_x8", warps, run([&](uint32_t* o, const uint32_t* i, long long* c) { k_indep<6, 8><<<grid, block>>>(o, i, c); }, grid, block, 8.0 * 4 * ITERS, nsm));
     emit("imad_wide_pair_x16", warps, run([&](uint32_t* o, const uint32_t* i, long long* c) { k_indep<6, 16><<<grid, block>>>(o, i, c); }, grid, block, 16.0 * 4 * ITERS, nsm));
+    emit("mul_wide_no_addend", warps, run([&](uint32_t* o, const uint32_t* i, long long* c) { k_indep<7, 8><<<grid, block>>>(o, i, c); }, grid, block, 8.0 * 4 * ITERS, nsm));
+    emit("imad_wide_pair_plus_2_iadd", warps, run([&](uint32_t* o, const uint32_t* i, long long* c) { k_indep<8, 8><<<grid, block>>>(o, i, c); }, grid, block, 8.0 * 4 * ITERS, nsm));
     emit("dfma", warps, run([&](uint32_t* o, const uint32_t* i, long long* c) { k_indep<3, 8><<<grid, block>>>(o, i, c); }, grid, block, 8.0 * 4 * ITERS, nsm));
     emit("shfl", warps, run([&](uint32_t* o, const uint32_t* i, long long* c) { k_indep<4, 8><<<grid, block>>>(o, i, c); }, grid, block, 8.0 * 4 * ITERS, nsm));
     emit("iadd_cc_pair", warps, run([&](uint32_t* o, const uint32_t* i, long long* c) { k_indep<5, 8><<<grid, block>>>(o, i, c); }, grid, block, 8.0 * 4 * ITERS * 2, nsm));
