@@ -11,7 +11,7 @@ kb = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 waves = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 fx = load_golden("vectors_%d.json" % kb)
 pub = pb.PublicContext(H(fx["n"])); priv = pb.PrivateContext(H(fx["p"]), H(fx["q"]))
-batch = int(148 * 224 * waves)
+batch = int(pub.wave() * waves)
 ln, lc = pub.n_limbs, pub.c_limbs
 rng = np.random.default_rng(1)
 m = rng.integers(0, 2**32, size=(batch, ln), dtype=np.uint32); m[:, kb // 32 - 1:] = 0

@@ -74,6 +74,51 @@ PAI_DEV void zero_tile(const Opnd& o, int t) {
   o.p[(2 * t + 1) * o.s] = z;
 }
 
+// Shared-memory operand addressed through the 32-bit shared window (LDS.128 / STS.128 with 32-bit address arithmetic)
+// instead of a generic 64-bit pointer: the hot loops of pai_tc.cuh load four quads per tile product, and with generic
+// pointers every one of them cost an IMAD.WIDE for the address on the very pipe the products run on, plus the longer
+// generic-load path.  The CPU simulation has no address spaces: there an SOpnd is an Opnd.
+#if !defined(PAI_HOSTSIM)
+struct SOpnd {
+  uint32_t a;      // shared address of quad 0
+  uint32_t sb;     // byte distance between consecutive quads
+};
+PAI_DEV SOpnd to_shared(const Opnd& o) {
+  SOpnd s;
+  s.a = (uint32_t)__cvta_generic_to_shared(o.p);
+  s.sb = (uint32_t)o.s * 16u;
+  return s;
+}
+PAI_DEV u4 lds_quad(uint32_t addr) {
+  u4 q;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
+  return q;
+}
+PAI_DEV void sts_quad(uint32_t addr, const u4& q) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+}
+PAI_DEV u4 ld_quad(const SOpnd& o, int q) { return lds_quad(o.a + (uint32_t)q * o.sb); }
+PAI_DEV void ld_tile(const SOpnd& o, int t, uint32_t a[8]) {
+  const uint32_t base = o.a + (uint32_t)(2 * t) * o.sb;
+  u4 q0 = lds_quad(base), q1 = lds_quad(base + o.sb);
+  a[0] = q0.x; a[1] = q0.y; a[2] = q0.z; a[3] = q0.w;
+  a[4] = q1.x; a[5] = q1.y; a[6] = q1.z; a[7] = q1.w;
+}
+PAI_DEV void st_tile(const SOpnd& o, int t, const uint32_t a[8]) {
+  const uint32_t base = o.a + (uint32_t)(2 * t) * o.sb;
+  u4 q0, q1;
+  q0.x = a[0]; q0.y = a[1]; q0.z = a[2]; q0.w = a[3];
+  q1.x = a[4]; q1.y = a[5]; q1.z = a[6]; q1.w = a[7];
+  sts_quad(base, q0);
+  sts_quad(base + o.sb, q1);
+}
+#else
+typedef Opnd SOpnd;
+PAI_DEV SOpnd to_shared(const Opnd& o) { return o; }
+PAI_DEV u4 ld_quad(const SOpnd& o, int q) { return o.p[q * o.s]; }
+#endif
+PAI_DEV u4 ld_quad_g(const Opnd& o, int q) { return o.p[q * o.s]; }
+
 // ------------------------------------------------------------------------------------------------
 // Carry-chain primitives.  Each is ONE asm block so the carry flag never crosses a statement.
 

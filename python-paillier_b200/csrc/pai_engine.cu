@@ -10,6 +10,7 @@
 #include "pai_rt.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <map>
 #include <mutex>
 #include <new>
@@ -51,6 +52,26 @@ struct EncDigitBody {
   const uint32_t* prog; int nops, nodd; const uint32_t* m; const uint32_t* r; uint32_t* out; long batch; u4* tbl;
   unsigned long long* counter; const uint32_t* gzero;
   PAI_MEM void run(u4* smem, const CtaId& id) const { cta_encrypt_digit<NTH>(smem, id, prog, nops, nodd, m, r, out, batch, tbl, counter, gzero); }
+};
+// tensor-core path (pai_tc.cuh)
+template <int NTH>
+struct TcSetupBody {
+  const uint32_t* consts; int const_quads;
+  const uint32_t* N; uint8_t* blob; uint32_t* scratch;
+  PAI_MEM void run(u4*, const CtaId& id) const { if (id.tid == 0 && id.cta == 0) tc_setup<NTH>(N, blob, scratch); }
+};
+template <int NTH>
+struct TcEncBody {
+  const uint32_t* consts; int const_quads;
+  const uint32_t* prog; int nops, nodd; const uint32_t* m; const uint32_t* r; uint32_t* out; long batch; u4* tbl;
+  const uint32_t* gzero; const uint8_t* bands; int stagger; long long* prof;
+  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_encrypt_tc<NTH>(smem, id, prog, nops, nodd, m, r, out, batch, tbl, gzero, bands, stagger, prof); }
+};
+template <int NTP, int W>
+struct TcDecBody {
+  const uint32_t* consts; int const_quads;
+  int nwin_p, nwin_q; const uint32_t* c; uint32_t* out; long batch; u4* tbl; const uint8_t* bands; int stagger;
+  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_decrypt_tc<NTP, W>(smem, id, nwin_p, nwin_q, c, out, batch, tbl, bands, stagger); }
 };
 template <int NTH, int W>
 struct PowDigitBody {
@@ -366,6 +387,9 @@ struct pai_pub {
   pai_mod* nmod = nullptr;          // modulus n with the digit-form constants appended (pai_digit.cuh)
   uint32_t* d_enc_consts = nullptr; // compact constant area of the encrypt kernel (dc_enc_limbs)
   bool use_digit = true;            // PAI_ENCRYPT_PATH=full selects the full-width Montgomery path instead
+  uint8_t* d_tc = nullptr;          // tensor-core path: [ band(N') | band(n) ] (pai_tc.cuh); null when not supported
+  bool use_tc = false;              // PAI_TC=0 disables it
+  int tc_stagger = 0;               // start-up delay (cycles) of the second thread group
   long wave = 0;                    // ciphertexts per wave of the throughput encrypt kernel (lazily measured)
 };
 struct pai_priv {
@@ -375,6 +399,9 @@ struct pai_priv {
   pai_mod *pd = nullptr, *qd = nullptr;   // p, q with digit-form constants (pai_digit.cuh)
   uint32_t* d_dconsts = nullptr;    // digit path: [ P: dblob(p) | hM | e ][ Q: ... ][ pinvqM ]
   bool use_digit = true;
+  uint8_t* d_tc = nullptr;          // tensor-core path: [ band(p') | band(p) | band(q') | band(q) ]; null when not supported
+  bool use_tc = false;
+  int tc_stagger = 0;
   int nwin_p = 0, nwin_q = 0;
   limbs_t h_p, h_q, h_pinv, h_hp, h_hq;   // 16*NTP limbs each (padded)
   DevBuf h_c, h_m;                  // staging of pai_decrypt_host (under `mu`)
@@ -431,7 +458,20 @@ struct pai_priv {
     default: g_err = "unsupported key size"; rc = PAI_E_ARG;                                          \
   }
 
+#define DISPATCH_TC(NTV, CALL)                                                                        \
+  switch (NTV) {                                                                                      \
+    case 2: { constexpr int NTH = 2; CALL; } break;                                                   \
+    case 4: { constexpr int NTH = 4; CALL; } break;                                                   \
+    case 6: { constexpr int NTH = 6; CALL; } break;                                                   \
+    case 8: { constexpr int NTH = 8; CALL; } break;                                                   \
+    case 12: { constexpr int NTH = 12; CALL; } break;                                                 \
+    default: g_err = "key size not supported by the tensor-core path"; rc = PAI_E_ARG;                \
+  }
+
 namespace {
+
+// tile counts the tensor-core kernels are instantiated for (DISPATCH_TC), up to `max_tiles`
+bool tc_supported(int tiles, int max_tiles) { return (tiles == 2 || tiles == 4 || tiles == 6 || tiles == 8 || tiles == 12) && tiles <= max_tiles; }
 
 template <int NT>
 int do_setup(pai_mod* m, rt_stream s) {
@@ -561,6 +601,90 @@ int do_encrypt_digit(pai_pub* k, const uint32_t* m_, const uint32_t* r, uint32_t
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
 }
 
+// launch geometry of a tensor-core kernel: 2 groups of 128 threads per CTA when shared memory allows, else 1
+template <class B, int NTH, class SmemFn>
+int tc_geometry_of(int device, SmemFn smem_bytes, long batch, Geom& g) {
+#if defined(PAI_HOSTSIM)
+  g.nthr = TC_RL;
+  g.smem = smem_bytes(TC_M);
+  long chunks = (batch + g.nthr - 1) / g.nthr;
+  g.grid = (int)std::max(1L, std::min(chunks, 3L));
+  (void)device;
+  return 0;
+#else
+  const size_t max_smem = rt_max_smem(device);
+  for (int nthr = 2 * TC_M; nthr >= TC_M; nthr -= TC_M) {
+    size_t smem = smem_bytes(nthr);
+    if (smem + 64 > max_smem || (nthr / TC_M) * 32 * NTH > 512) continue;      // shared memory, TMEM columns
+    int occ = rt_occupancy<B>(nthr, smem);
+    if (occ <= 0) continue;
+    occ = std::min(occ, 512 / tc_tmem_cols<NTH>(nthr / TC_M));     // TMEM columns of the SM
+    long chunks = (batch + nthr - 1) / nthr;
+    g.nthr = nthr; g.smem = smem;
+    g.grid = (int)std::max(1L, std::min(chunks, (long)rt_sm_count(device) * occ));
+    return 0;
+  }
+  g_err = "tensor-core kernel cannot be resident";
+  return PAI_E_CUDA;
+#endif
+}
+template <int NTH>
+int tc_geometry(pai_pub* k, long batch, Geom& g) {
+  return tc_geometry_of<TcEncBody<NTH>, NTH>(k->nmod->device, [](int nthr) { return tc_enc_smem_bytes<NTH>(nthr); }, batch, g);
+}
+template <int NTH>
+int do_encrypt_tc(pai_pub* k, const uint32_t* m_, const uint32_t* r, uint32_t* c, long batch, rt_stream s) {
+  typedef TcEncBody<NTH> B;
+  pai_mod* m = k->nmod;
+  Geom g;
+  int rc = tc_geometry<NTH>(k, batch, g);
+  if (rc) return rc;
+  rc = m->ws.get(s).tbl.ensure((size_t)g.grid * (size_t)(k->nodd + 2) * 4 * NTH * g.nthr * 16);
+  if (rc) return rc;
+  B body{k->d_enc_consts, dc_enc_limbs(NTH) / 4, k->d_prog, k->nops, k->nodd, m_, r, c, batch, (u4*)m->ws.get(s).tbl.p,
+         m->d_blob + dc_zero_offset(NTH), k->d_tc, k->tc_stagger, nullptr};
+#if !defined(PAI_HOSTSIM)
+  // development aid: PAI_TC_PROF=<file> dumps per-warp cycle counters of the phases of tc_op after a synchronous launch
+  if (const char* pf = getenv("PAI_TC_PROF")) {
+    const size_t nw = (size_t)g.grid * (g.nthr / 32), bytes = nw * 16 * sizeof(long long);
+    void* d = nullptr;
+    rc = rt_malloc(&d, bytes);
+    if (!rc) rc = rt_memset(d, 0, bytes, s);
+    body.prof = (long long*)d;
+    if (!rc) rc = rt_launch_group(body, g.grid, g.nthr, g.smem, s);
+    std::vector<long long> h(nw * 16);
+    if (!rc) rc = rt_d2h(h.data(), d, bytes, s);
+    if (!rc) rc = rt_sync(s);
+    if (!rc) if (FILE* f = fopen(pf, "w")) {
+      for (size_t w = 0; w < nw; w++) { for (int i = 0; i < 16; i++) fprintf(f, "%lld ", h[w * 16 + i]); fprintf(f, "\n"); }
+      fclose(f);
+    }
+    rt_free(d);
+    return rc;
+  }
+#endif
+  return rt_launch_group(body, g.grid, g.nthr, g.smem, s);
+}
+template <int NTH>
+long encrypt_wave_tc(pai_pub* k) {
+  Geom g;
+  if (tc_geometry<NTH>(k, 1L << 40, g)) return 0;
+  return (long)g.grid * g.nthr;
+}
+template <int NTH>
+int do_tc_setup(pai_pub* k, rt_stream s) {
+  void* scratch = nullptr;
+  int rc = rt_malloc(&scratch, (size_t)8 * NTH * 4);
+  if (!rc) rc = rt_malloc((void**)&k->d_tc, (size_t)tc_blob_bytes(NTH));
+  if (!rc) {
+    TcSetupBody<NTH> b{nullptr, 0, k->nmod->d_blob, k->d_tc, (uint32_t*)scratch};
+    rc = rt_launch(b, 1, 32, 0, s);
+  }
+  if (!rc) rc = rt_sync(s);
+  rt_free(scratch);
+  return rc;
+}
+
 template <class B>
 long wave_of(int device, int NT, int cq, int nbuf) {
   Geom g;
@@ -618,6 +742,43 @@ int do_decrypt_digit(pai_priv* k, const uint32_t* c, uint32_t* out, long batch, 
   if (rc) return rc;
   B body{k->d_dconsts, cq, k->nwin_p, k->nwin_q, c, out, batch, (u4*)k->ws.get(s).tbl.p, ctr};
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
+}
+
+template <int NTP>
+int tc_dec_geometry(pai_priv* k, long batch, Geom& g) {
+  return tc_geometry_of<TcDecBody<NTP, W_DEC>, NTP>(k->device, [](int nthr) { return tc_dec_smem_bytes<NTP>(nthr); }, batch, g);
+}
+template <int NTP>
+int do_decrypt_tc(pai_priv* k, const uint32_t* c, uint32_t* out, long batch, rt_stream s) {
+  typedef TcDecBody<NTP, W_DEC> B;
+  Geom g;
+  int rc = tc_dec_geometry<NTP>(k, batch, g);
+  if (rc) return rc;
+  rc = k->ws.get(s).tbl.ensure((size_t)g.grid * (((size_t)1 << W_DEC) + 1) * 4 * NTP * g.nthr * 16);
+  if (rc) return rc;
+  int cq = 2 * (dside_limbs<NTP>() / 4) + 2 * NTP;
+  B body{k->d_dconsts, cq, k->nwin_p, k->nwin_q, c, out, batch, (u4*)k->ws.get(s).tbl.p, k->d_tc, k->tc_stagger};
+  return rt_launch_group(body, g.grid, g.nthr, g.smem, s);
+}
+template <int NTP>
+long decrypt_wave_tc(pai_priv* k) {
+  Geom g;
+  if (tc_dec_geometry<NTP>(k, 1L << 40, g)) return 0;
+  return (long)g.grid * g.nthr;
+}
+template <int NTP>
+int do_priv_tc_setup(pai_priv* k, rt_stream s) {
+  void* scratch = nullptr;
+  int rc = rt_malloc(&scratch, (size_t)8 * NTP * 4);
+  if (!rc) rc = rt_malloc((void**)&k->d_tc, (size_t)2 * tc_blob_bytes(NTP));
+  pai_mod* md[2] = {k->pd, k->qd};
+  for (int i = 0; i < 2 && !rc; i++) {
+    TcSetupBody<NTP> b{nullptr, 0, md[i]->d_blob, k->d_tc + (size_t)i * tc_blob_bytes(NTP), (uint32_t*)scratch};
+    rc = rt_launch(b, 1, 32, 0, s);
+    if (!rc) rc = rt_sync(s);
+  }
+  rt_free(scratch);
+  return rc;
 }
 
 // digit-form constants of the private key, assembled from the digit blobs of p and q and from the
@@ -854,7 +1015,8 @@ static int do_coop_decrypt_pow(pai_priv* k, const uint32_t* d_c, uint32_t* up, u
 static int pub_wave(pai_pub* k) {
   int rc = 0;
   if (!k->wave) {
-    if (k->use_digit) { DISPATCH_NTH(k->nmod->NT, k->wave = encrypt_wave_digit<NTH>(k)); }
+    if (k->use_tc) { DISPATCH_TC(k->nmod->NT, k->wave = encrypt_wave_tc<NTH>(k)); }
+    else if (k->use_digit) { DISPATCH_NTH(k->nmod->NT, k->wave = encrypt_wave_digit<NTH>(k)); }
     else { DISPATCH_NT(k->nsq->NT, k->wave = (wave_of<EncBody<NT>>(k->nsq->device, NT, mc_limbs(NT) / 4 + NT, 2))); }
     if (rc) return rc;
     if (k->wave <= 0) k->wave = 1;
@@ -864,7 +1026,8 @@ static int pub_wave(pai_pub* k) {
 static int priv_wave(pai_priv* k) {
   int rc = 0;
   if (!k->wave) {
-    if (k->use_digit) { DISPATCH_NTP(k->NTP, k->wave = (wave_of<DecDigitBody<NTP, W_DEC>>(k->device, 2 * NTP, 2 * (dside_limbs<NTP>() / 4) + 2 * NTP, 2))); }
+    if (k->use_tc) { DISPATCH_TC(k->NTP, k->wave = decrypt_wave_tc<NTH>(k)); }
+    else if (k->use_digit) { DISPATCH_NTP(k->NTP, k->wave = (wave_of<DecDigitBody<NTP, W_DEC>>(k->device, 2 * NTP, 2 * (dside_limbs<NTP>() / 4) + 2 * NTP, 2))); }
     else { DISPATCH_NTP(k->NTP, k->wave = (wave_of<DecBody<NTP, W_DEC>>(k->device, 2 * NTP, 2 * (mc_limbs(2 * NTP) / 4 + mc_limbs(NTP) / 4 + 6 * NTP) + 2 * NTP, 3))); }
     if (rc) return rc;
     if (k->wave <= 0) k->wave = 1;
@@ -998,6 +1161,15 @@ int pai_pub_create(const uint32_t* n, int limbs, int device, pai_pub** out) {
     if (!rc) rc = rt_d2d(c + 9 * h + 16, e + 6 * h, (size_t)2 * h * 4, 0);         // E3
   }
   { const char* e = getenv("PAI_ENCRYPT_PATH"); k->use_digit = !(e && std::string(e) == "full"); }
+  // tensor-core reductions (pai_tc.cuh): digit moduli of at most 384 base-256 digits (keys up to 3072 bits; above that
+  // the operand buffers of even one 128-thread group no longer fit shared memory)
+  if (!rc && tc_supported(2 * ntp, 12)) {
+    DISPATCH_TC(2 * ntp, rc = do_tc_setup<NTH>(k, 0));
+    const char* e = getenv("PAI_TC");
+    k->use_tc = !rc && k->use_digit && !(e && std::string(e) == "0");
+    const char* st = getenv("PAI_TC_STAGGER");
+    k->tc_stagger = st && *st ? atoi(st) : 40000;
+  }
   // exponent program for r^n: sliding windows of W_ENC bits over the public exponent n
   std::vector<uint32_t> prog = sliding_program(nn, W_ENC);
   k->nops = (int)prog.size();
@@ -1015,6 +1187,7 @@ int pai_pub_destroy(pai_pub* k) {
   rt_free(k->d_nth);
   rt_free(k->d_prog);
   rt_free(k->d_enc_consts);
+  rt_free(k->d_tc);
   k->ws.release(); k->h_m.release(); k->h_r.release(); k->h_c.release(); k->h_s.release();
   mod_free(k->nsq);
   mod_free(k->nmod);
@@ -1051,7 +1224,8 @@ int pai_encrypt(pai_pub* k, const uint32_t* d_m, const uint32_t* d_r, uint32_t* 
     if (rc || off == 0) return rc;
     batch = off;
   }
-  if (k->use_digit) { DISPATCH_NTH(k->nmod->NT, rc = do_encrypt_digit<NTH>(k, d_m, d_r, d_c, batch, (rt_stream)stream)); }
+  if (k->use_tc) { DISPATCH_TC(k->nmod->NT, rc = do_encrypt_tc<NTH>(k, d_m, d_r, d_c, batch, (rt_stream)stream)); }
+  else if (k->use_digit) { DISPATCH_NTH(k->nmod->NT, rc = do_encrypt_digit<NTH>(k, d_m, d_r, d_c, batch, (rt_stream)stream)); }
   else { DISPATCH_NT(k->nsq->NT, rc = do_encrypt<NT>(k, d_m, d_r, d_c, batch, (rt_stream)stream)); }
   return rc;
 }
@@ -1167,6 +1341,13 @@ int pai_priv_create(const uint32_t* p, const uint32_t* q, int limbs, int device,
   if (!rc) { DISPATCH_NTP(ntp, rc = do_priv_setup<NTP>(k, 0)); }
   if (!rc) { DISPATCH_NTP(ntp, rc = do_priv_digit_setup<NTP>(k, 0)); }
   { const char* e = getenv("PAI_DECRYPT_PATH"); k->use_digit = !(e && std::string(e) == "full"); }
+  if (!rc && tc_supported(ntp, 8)) {            // tensor-core reductions: p, q of 64 .. 256 base-256 digits (keys up to 4096 bits)
+    DISPATCH_TC(ntp, rc = do_priv_tc_setup<NTH>(k, 0));
+    const char* e = getenv("PAI_TC");
+    k->use_tc = !rc && k->use_digit && !(e && std::string(e) == "0");
+    const char* st = getenv("PAI_TC_STAGGER");
+    k->tc_stagger = st && *st ? atoi(st) : 40000;
+  }
   if (rc) { pai_priv_destroy(k); return rc; }
   *out = k;
   return 0;
@@ -1186,6 +1367,7 @@ int pai_priv_destroy(pai_priv* k) {
     rt_sync(0);
   }
   rt_free(k->d_dconsts);
+  if (k->d_tc) { rt_memset(k->d_tc, 0, (size_t)2 * tc_blob_bytes(k->NTP), 0); rt_sync(0); rt_free(k->d_tc); }
   if (k->d_coop_e) { rt_memset(k->d_coop_e, 0, (size_t)16 * k->NTP * 4, 0); rt_sync(0); rt_free(k->d_coop_e); }
   mod_free(k->pd); mod_free(k->qd);
   k->ws.release(); k->h_c.release(); k->h_m.release();
@@ -1251,7 +1433,8 @@ int pai_decrypt(pai_priv* k, const uint32_t* d_c, uint32_t* d_m, long batch, voi
     if (rc || off == 0) return rc;
     batch = off;
   }
-  if (k->use_digit) { DISPATCH_NTP(k->NTP, rc = do_decrypt_digit<NTP>(k, d_c, d_m, batch, (rt_stream)stream)); }
+  if (k->use_tc) { DISPATCH_TC(k->NTP, rc = do_decrypt_tc<NTH>(k, d_c, d_m, batch, (rt_stream)stream)); }
+  else if (k->use_digit) { DISPATCH_NTP(k->NTP, rc = do_decrypt_digit<NTP>(k, d_c, d_m, batch, (rt_stream)stream)); }
   else { DISPATCH_NTP(k->NTP, rc = do_decrypt<NTP>(k, d_c, d_m, batch, (rt_stream)stream)); }
   return rc;
 }

@@ -91,6 +91,9 @@ static inline int rt_launch(const Body& b, int grid, int nthr, size_t smem, rt_s
 // warp-cooperative bodies (pai_coop.cuh): every thread runs the body, lanes cooperate through shuffles
 template <class Body>
 static inline int rt_launch_coop(const Body& b, int grid, int nthr, size_t smem, rt_stream s) { return rt_launch(b, grid, nthr, smem, s); }
+// group-cooperative bodies (pai_tc.cuh): every thread runs the body, 128-thread groups cooperate through the tensor cores
+template <class Body>
+static inline int rt_launch_group(const Body& b, int grid, int nthr, size_t smem, rt_stream s) { return rt_launch(b, grid, nthr, smem, s); }
 
 #else
 // ------------------------------------------------------------------------------------ host simulation (tests only)
@@ -126,6 +129,18 @@ static inline int rt_launch_coop(const Body& b, int grid, int nthr, size_t smem,
   std::vector<u4> sm(smem / 16 + 1);
   for (int cta = 0; cta < grid; cta++)
     for (int warp = 0; warp < nthr / 32; warp++) { CtaId id{warp * 32, nthr, cta, grid}; b.run(sm.data(), id); }
+  g_launches++;
+  return 0;
+}
+// group-cooperative bodies: one call per CTA walks the rows of its group phase by phase (row arrays, pai_tc.cuh)
+template <class Body>
+static inline int rt_launch_group(const Body& b, int grid, int nthr, size_t smem, rt_stream) {
+  std::vector<u4> sm(smem / 16 + 16);
+  for (int cta = 0; cta < grid; cta++) {
+    for (int tid = 0; tid < nthr; tid++) { CtaId id{tid, nthr, cta, grid}; cta_load_consts(sm.data(), id, b.consts, b.const_quads); }
+    CtaId id{0, nthr, cta, grid};
+    b.run(sm.data(), id);
+  }
   g_launches++;
   return 0;
 }

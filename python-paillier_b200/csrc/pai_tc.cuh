@@ -1,0 +1,794 @@
+// pai_tc.cuh -- digit Montgomery arithmetic modulo n^2 with the REDUCTIONS on the 5th-generation tensor cores.
+//
+// Every Montgomery reduction multiplies a per-ciphertext number by a batch-wide constant twice:
+//     m = T_lo * N' mod R        (N' = -n^-1 mod R)          and          hi = floor(m * n / R).
+// In base-256 digits, for the 128 ciphertexts of a thread group at once, that is  [128 x D] x Toeplitz(const):
+// one tcgen05.mma kind::i8 GEMM each (M = 128 TMEM lanes = 128 ciphertexts, N = D digit columns, K = D digits, u8 x u8
+// -> s32 column sums <= D * 255^2 < 2^24).  The thread that owns row i reads its column sums back with tcgen05.ld,
+// propagates the carries (ALU pipe) and has the quotient / the high half as ordinary 32-bit limbs again.  What stays on
+// the integer-multiply pipe are only the products of two per-ciphertext numbers (x0*y0, x0*y1 + x1*y0): 100 instead
+// of 228 tile products per squaring, 192 instead of 320 per multiplication at 2048-bit keys, and no quotient products.
+//
+// Exactness of the high half.  GEMM 2 produces the byte columns D-4 .. 2D-5 of m*n (the top three columns 2D-4 .. 2D-2
+// are six scalar byte products).  The columns below D-4 are never computed: their sum I is < 1.004 * 256^(D-2), and the
+// low half of m*n is KNOWN, m*n mod R = -T_lo mod R =: L.  With S the exactly propagated part (columns >= D-4),
+// s = its guard limb (digits D-4 .. D-1) and l the top limb of L:   floor(m*n / R) = floor(S / R) + [s > l]
+// (S mod R + I wraps past R exactly when the guard limb exceeds l; checked against integers in tests/test_tc_model.py).
+//
+// Data flow of one product Z = X*Y*R^-1 mod n^2 (digits X = x0 + n x1 etc., see pai_digit.cuh for the identity):
+//   P1  T = x0*y0            (IMAD)   T_lo -> A (the group's MMA operand buffer, row = thread), T_hi -> park (L2)
+//   G1  A x Toeplitz(N')     (tensor) E1: m -> A (digits == limb bytes: the buffer is both operand and limb array)
+//   G2  A x Toeplitz(n)      (tensor) E2: t = T_hi + hi + [T_lo != 0] -> park;  carry = [t >= n];  A <- W = K - m
+//   P2  B = x0*y1 + x1*y0 + W (IMAD)  B_lo -> A (over W, tile by tile), B_hi -> over x0 (dead tile by tile)
+//   G1  A x Toeplitz(N')              E1: m' -> A
+//   G2  A x Toeplitz(n)               E4: z = B_hi + hi' + ... (< 3n + 3) -> Z1 in place, reduced by digit_reduce3
+//   Z0 = t - n*carry: park -> the buffer of x1.       Shared memory per ciphertext: 3 half-buffers (x0, x1, A).
+//
+// A CTA runs two independent groups of 128 threads (named barriers, own mbarrier, own 256 TMEM columns): while one
+// group waits for its GEMMs and runs the ALU epilogues, the other one keeps the integer-multiply pipe busy.
+//
+// Compiled twice like everything else: nvcc (sm_100a: tcgen05 / TMEM / mbarrier inline PTX) and g++ -DPAI_HOSTSIM, where
+// a "group" is 8 rows walked phase by phase and the GEMM is an integer loop over the very same operand layouts.
+#pragma once
+#include "pai_digit.cuh"
+
+namespace pai {
+
+#if defined(PAI_HOSTSIM)
+constexpr int TC_RL = 4;                  // rows of a group the simulation walks (placed in varying 8-row groups of the layout)
+#else
+constexpr int TC_RL = 1;                  // the GPU thread owns one row; state lives in registers
+#endif
+#define TC_EACH_ROW for (int rw = 0; rw < TC_RL; rw++)
+constexpr int TC_M = 128;                 // rows (ciphertexts) of a group = TMEM lanes
+
+// ---- operand layouts (K-major, no swizzle: 8 x 16-byte core matrices) ---------------------------------------------
+// A operand [128 x D]: digit k of row r.  Core matrix (r/8, k/16) at ((r/8) * (D/16) + k/16) * 128 bytes.
+PAI_HD uint32_t tc_a_off(int D, int r, int k) {
+  return ((uint32_t)(r >> 3) * (uint32_t)(D / 16) + (uint32_t)(k >> 4)) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(k & 15);
+}
+// Toeplitz operands are stored as BANDS: for the K block kappa (digits 32 kappa .. 32 kappa + 31) the [D x 32] tile of
+// Toeplitz(c)[j][k] = c[j - k + shift] only depends on j - 32 kappa, so all K blocks read windows of ONE [2D-32 x 32]
+// matrix band[u][k'] = c[u - (D - 32) + shift - k'], window of block kappa = rows u0 .. u0 + D - 1, u0 = D - 32 - 32 kappa.
+// 15 KB per constant at 2048-bit keys instead of a 64 KB D x D matrix.
+PAI_HD int tc_band_rows(int NTH) { return 64 * NTH - 32; }
+PAI_HD int tc_band_bytes(int NTH) { return 32 * tc_band_rows(NTH); }
+PAI_HD uint32_t tc_band_off(int u, int kp) {
+  return ((uint32_t)(u >> 3) * 2u + (uint32_t)(kp >> 4)) * 128u + (uint32_t)(u & 7) * 16u + (uint32_t)(kp & 15);
+}
+// global blob of one modulus for this path: [ band(N') | band(n) ]
+PAI_HD int tc_blob_bytes(int NTH) { return 2 * tc_band_bytes(NTH); }
+
+// single-thread setup: N' = -n^-1 mod 256^D, then the two bands.  scratch: 8*NTH limbs.
+template <int NTH>
+PAI_DEV void tc_setup(const uint32_t* N, uint8_t* blob, uint32_t* scratch) {
+  const int D = 32 * NTH, L = 8 * NTH;
+  inv_mod_2k(scratch, N, L);
+  uint32_t c = 1;
+  for (int i = 0; i < L; i++) { uint64_t v = (uint64_t)(~scratch[i]) + c; scratch[i] = (uint32_t)v; c = (uint32_t)(v >> 32); }
+  const uint8_t* np = (const uint8_t*)scratch;       // little-endian limbs == base-256 digits
+  const uint8_t* nb = (const uint8_t*)N;
+  uint8_t* b1 = blob;
+  uint8_t* b2 = blob + tc_band_bytes(NTH);
+  const int U = tc_band_rows(NTH);
+  for (int u = 0; u < U; u++)
+    for (int kp = 0; kp < 32; kp++) {
+      int i1 = u - (D - 32) - kp;                      // N'[j - k]
+      int i2 = u + 28 - kp;                            // n[(D - 4 + j') - k]
+      b1[tc_band_off(u, kp)] = (i1 >= 0 && i1 < D) ? np[i1] : 0;
+      b2[tc_band_off(u, kp)] = (i2 >= 0 && i2 < D) ? nb[i2] : 0;
+    }
+}
+
+// ---- per-group context -------------------------------------------------------------------------------------------
+template <int NTH>
+struct TcCtx {
+  DigitEnv* dc;
+  u4* H[2];                 // shared half-buffers, interleaved: quad q of thread t at H[i][q * nthr + t]
+  u4* A;                    // this group's operand buffer (128 * D bytes, tc_a_off layout)
+  const uint8_t* band[2];   // shared: band(N'), band(n)
+  Opnd tbl;                 // window table of THIS thread (global, stride nthr); simulation: of row 0
+  int slots;                // table entries; entry `slots` is the park slot
+  int tid, nthr;            // thread index in the CTA / threads per CTA (simulation: 0 / TC_RL)
+  int row0;                 // row of this thread inside the group (simulation: first of the TC_RL rows)
+#if defined(PAI_HOSTSIM)
+  int32_t tmem[TC_RL][512];
+#else
+  uint32_t tmem;            // TMEM address of this group's accumulator (lane 0, first column)
+  uint64_t* mbar;           // the group's mbarrier
+  uint32_t phase;
+  int grp;                  // group index (named barrier 1 + grp)
+  long long* prof;          // optional phase profile (PAI_TC_PROF): 16 cycle counters per warp, or null
+#endif
+};
+
+// phase timing (development aid): adds the cycles since *t to counter i of this warp and restarts the clock
+#if !defined(PAI_HOSTSIM)
+#define TC_PROF_START(c, t) long long t = (c).prof ? clock64() : 0
+#define TC_PROF(c, t, i) do { if ((c).prof) { long long n_ = clock64(); if ((threadIdx.x & 31) == 0) (c).prof[i] += n_ - t; t = n_; } } while (0)
+#else
+#define TC_PROF_START(c, t) (void)0
+#define TC_PROF(c, t, i) (void)0
+#endif
+
+template <int NTH>
+PAI_DEV Opnd tc_h(const TcCtx<NTH>& c, int i, int rw) { Opnd o; o.p = c.H[i] + c.tid + rw; o.s = c.nthr; return o; }
+template <int NTH>
+PAI_DEV Opnd tc_a(const TcCtx<NTH>& c, int rw) {
+  const int r = c.row0 + rw;
+  Opnd o; o.p = c.A + (size_t)(r >> 3) * (2 * NTH) * 8 + (r & 7); o.s = 8; return o;
+}
+template <int NTH>
+PAI_DEV Opnd tc_tbl(const TcCtx<NTH>& c, int e, int half, int rw) {
+  Opnd o; o.p = c.tbl.p + rw + ((size_t)e * 4 * NTH + (size_t)half * 2 * NTH) * c.tbl.s; o.s = c.tbl.s; return o;
+}
+template <int NTH>
+PAI_DEV Opnd tc_park(const TcCtx<NTH>& c, int rw) { return tc_tbl<NTH>(c, c.slots, 0, rw); }
+template <int NTH>
+PAI_DEV SOpnd tc_hs(const TcCtx<NTH>& c, int i, int rw) { return to_shared(tc_h<NTH>(c, i, rw)); }
+template <int NTH>
+PAI_DEV SOpnd tc_as(const TcCtx<NTH>& c, int rw) { return to_shared(tc_a<NTH>(c, rw)); }
+
+// state of one row between the phases of one product
+struct TcRow {
+  uint32_t ltop, nz, carry, wtop, ovf2;
+};
+
+// ---- tensor-core plumbing ------------------------------------------------------------------------------------------
+#if !defined(PAI_HOSTSIM)
+PAI_DEV uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// K-major, no-swizzle shared-memory matrix descriptor: LBO = byte distance of core matrices along K, SBO = along M/N
+PAI_DEV uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;                                 // descriptor version of sm_100
+  return d;
+}
+// instruction descriptor: D = s32, A = B = unsigned 8 bit, both K-major, dense
+PAI_DEV uint32_t tc_idesc(int n, int m) { return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
+PAI_DEV void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+PAI_DEV void tc_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count));
+}
+PAI_DEV void tc_mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tTC_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra TC_DONE;\n\tbra TC_WAIT;\n\tTC_DONE:\n\t}\n" ::"r"(tc_smem_u32(bar)), "r"(phase)
+      : "memory");
+}
+PAI_DEV void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+PAI_DEV void tc_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+#endif
+
+// 32 consecutive column sums of this thread's row, starting at column c0
+template <int NTH>
+PAI_DEV void tc_ld32(const TcCtx<NTH>& c, int rw, int c0, uint32_t v[32]) {
+#if defined(PAI_HOSTSIM)
+  for (int j = 0; j < 32; j++) v[j] = (uint32_t)c.tmem[rw][c0 + j];
+#else
+  (void)rw;
+  const uint32_t taddr = c.tmem + (((uint32_t)(c.row0 & ~31)) << 16) + (uint32_t)c0;      // lane quarter of this warp
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#endif
+}
+
+// The group's GEMM: accumulator = A x window(band[which]).  All threads of the group call it.
+template <int NTH>
+PAI_DEV void tc_gemm(TcCtx<NTH>& c, int which) {
+  const int D = 32 * NTH;
+#if defined(PAI_HOSTSIM)
+  const uint8_t* a = (const uint8_t*)c.A;
+  TC_EACH_ROW {
+    const int r = c.row0 + rw;
+    for (int j = 0; j < D; j++) {
+      int64_t sum = 0;
+      for (int kap = 0; kap < NTH; kap++) {
+        const int u0 = D - 32 - 32 * kap;
+        for (int kp = 0; kp < 32; kp++)
+          sum += (int64_t)a[tc_a_off(D, r, 32 * kap + kp)] * c.band[which][tc_band_off(u0 + j, kp)];
+      }
+      c.tmem[rw][j] = (int32_t)sum;
+    }
+  }
+#else
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy writes of A -> tensor-core reads
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");    // our tcgen05.ld of the previous accumulator are done
+  tc_bar_sync(1 + c.grp, TC_M);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (c.row0 == 0) {
+    // one MMA covers at most 256 columns: wider moduli (D = 384 at 3072-bit keys) take two column blocks per K step
+    const uint32_t a0 = tc_smem_u32(c.A), b0 = tc_smem_u32(c.band[which]);
+#pragma unroll
+    for (int kap = 0; kap < NTH; kap++) {
+      const uint64_t da = tc_desc(a0 + (uint32_t)kap * 2u * 128u, 128u, (uint32_t)(D / 16) * 128u);
+#pragma unroll
+      for (int n0 = 0; n0 < D; n0 += 256) {
+        const int nn = D - n0 < 256 ? D - n0 : 256;
+        const uint64_t db = tc_desc(b0 + (uint32_t)((D - 32 - 32 * kap + n0) / 8) * 256u, 128u, 256u);
+        tc_mma(c.tmem + (uint32_t)n0, da, db, tc_idesc(nn, TC_M), kap > 0 ? 1u : 0u);
+      }
+    }
+    tc_commit(c.mbar);
+  }
+  tc_mbar_wait(c.mbar, c.phase);
+  c.phase ^= 1u;
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#endif
+}
+
+// eight 32-bit limbs from 32 byte-column sums (each < 2^24) and the running carry.
+// On the GPU this is spelled in funnel shifts and add-with-carry chains so that it runs on the ALU pipe: written as 64-bit
+// C arithmetic ptxas turned the shifts into IMAD.WIDE (three per limb), i.e. onto the very pipe the products need.
+PAI_DEV void tc_limbs8(const uint32_t v[32], uint32_t& carry, uint32_t out[8]) {
+  PAI_UNROLL
+  for (int j = 0; j < 8; j++) {
+#if defined(PAI_HOSTSIM)
+    uint64_t x = (uint64_t)v[4 * j] + ((uint64_t)v[4 * j + 1] << 8) + ((uint64_t)v[4 * j + 2] << 16) + ((uint64_t)v[4 * j + 3] << 24) + carry;
+    out[j] = (uint32_t)x;
+    carry = (uint32_t)(x >> 32);
+#else
+    uint32_t lo, hi;
+    asm("{\n\t.reg .u32 t1, t2, t3, h2, h3;\n\t"
+        "shf.l.wrap.b32 t1, 0, %3, 8;\n\t"          // v1 << 8   (v1 < 2^24: no high part)
+        "shf.l.wrap.b32 t2, 0, %4, 16;\n\t"         // low word of v2 << 16
+        "shf.r.wrap.b32 h2, %4, 0, 16;\n\t"         // v2 >> 16
+        "shf.l.wrap.b32 t3, 0, %5, 24;\n\t"         // low word of v3 << 24
+        "shf.r.wrap.b32 h3, %5, 0, 8;\n\t"          // v3 >> 8
+        "add.cc.u32 %0, %2, t1;\n\t"
+        "addc.u32 %1, h2, h3;\n\t"
+        "add.cc.u32 %0, %0, t2;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        "add.cc.u32 %0, %0, t3;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        "add.cc.u32 %0, %0, %6;\n\t"
+        "addc.u32 %1, %1, 0;\n\t}"
+        : "=&r"(lo), "=&r"(hi)
+        : "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]), "r"(carry));
+    out[j] = lo;
+    carry = hi;
+#endif
+  }
+}
+
+// ---- phases ---------------------------------------------------------------------------------------------------------
+PAI_DEV uint32_t tc_or8(const uint32_t v[8], int n) { uint32_t o = 0; for (int i = 0; i < n; i++) o |= v[i]; return o; }
+
+// bookkeeping of a finished low half: nz = [lo != 0], ltop = top limb of (-lo mod R)
+struct TcLow {
+  uint32_t lowor, top;
+};
+PAI_DEV void tc_low_tile(TcLow& l, const uint32_t v[8], bool last) {
+  if (!last) l.lowor |= tc_or8(v, 8);
+  else { l.lowor |= tc_or8(v, 7); l.top = v[7]; }
+}
+
+// P1 (multiplication): T = x0 * y0;  T_lo -> A, T_hi + [T_lo != 0] -> park
+template <int NTH, class XT>
+PAI_FN void tc_prod1_mul(SOpnd A, Opnd P, XT x0, Opnd y0, TcRow* st) {
+  Acc acc;
+  acc_clear(acc);
+  TcLow low; low.lowor = 0; low.top = 0;
+  for (int k = 0; k < 2 * NTH; k++) {
+    int lo = k - NTH + 1 > 0 ? k - NTH + 1 : 0;
+    int hi = k < NTH ? k : NTH - 1;
+    for (int i = lo; i <= hi; i++) {
+      uint32_t x[8], y[8];
+      ld_tile(x0, i, x); ld_tile(y0, k - i, y);
+      tile_mac(acc, x, y);
+    }
+    if (k == NTH) acc.C[0] += st->nz;
+    uint32_t v[8];
+    acc_resolve_low(acc, v);
+    if (k < NTH) {
+      st_tile(A, k, v);
+      tc_low_tile(low, v, k == NTH - 1);
+      if (k == NTH - 1) { st->nz = (low.lowor | low.top) != 0u; st->ltop = ~low.top + (low.lowor == 0u ? 1u : 0u); }
+    } else {
+      st_tile(P, k - NTH, v);
+    }
+    acc_shift8(acc);
+  }
+}
+
+// P1 (squaring): T = x0^2 with the off-diagonal tile products taken once (doubled through S)
+template <int NTH>
+PAI_FN void tc_prod1_sqr(SOpnd A, Opnd P, SOpnd x0, TcRow* st) {
+  Acc acc, S;
+  acc_clear(acc);
+  acc_clear(S);
+  uint32_t topbit = 0;
+  TcLow low; low.lowor = 0; low.top = 0;
+  for (int k = 0; k < 2 * NTH; k++) {
+    int lo = k - NTH + 1 > 0 ? k - NTH + 1 : 0;
+    int hs = k == 0 ? -1 : (k - 1) / 2;
+    for (int i = lo; i <= hs; i++) {
+      uint32_t x[8], y[8];
+      ld_tile(x0, i, x); ld_tile(x0, k - i, y);
+      tile_mac(S, x, y);
+    }
+    if ((k & 1) == 0) {
+      uint32_t x[8];
+      ld_tile(x0, k >> 1, x);
+      tile_mac(acc, x, x);
+    }
+    {
+      uint32_t d[8], d2[8];
+      acc_resolve_low(S, d);
+      acc_shift8(S);
+      d2[0] = (d[0] << 1) | topbit;
+      PAI_UNROLL
+      for (int j = 1; j < 8; j++) d2[j] = (d[j] << 1) | (d[j - 1] >> 31);
+      topbit = d[7] >> 31;
+      acc_add_low(acc, d2);
+    }
+    if (k == NTH) acc.C[0] += st->nz;
+    uint32_t v[8];
+    acc_resolve_low(acc, v);
+    if (k < NTH) {
+      st_tile(A, k, v);
+      tc_low_tile(low, v, k == NTH - 1);
+      if (k == NTH - 1) { st->nz = (low.lowor | low.top) != 0u; st->ltop = ~low.top + (low.lowor == 0u ? 1u : 0u); }
+    } else {
+      st_tile(P, k - NTH, v);
+    }
+    acc_shift8(acc);
+  }
+}
+
+// E1: quotient m = (column sums of lo * N') mod R -> A (as limbs == digits)
+template <int NTH>
+PAI_FN void tc_epi_m(const TcCtx<NTH>* c, int rw, SOpnd A) {
+  uint32_t carry = 0;
+  for (int t = 0; t < NTH; t++) {
+    uint32_t v[32], l[8];
+    tc_ld32<NTH>(*c, rw, 32 * t, v);
+    tc_limbs8(v, carry, l);
+    st_tile(A, t, l);
+  }
+}
+
+// the high half of m*n, one tile at a time: hi tile j = S-limbs 8j+1 .. 8j+8 (S-limb 0 is the guard limb), the very top
+// limb from the three scalar columns.  Usage: tc_hi_begin, then tc_hi_tile for j = 0 .. NTH-1.
+template <int NTH>
+struct TcHi {
+  uint32_t L[8];
+  uint32_t carry;
+  uint32_t cadd;          // [guard limb > ltop]
+};
+template <int NTH>
+PAI_DEV void tc_hi_begin(const TcCtx<NTH>& c, int rw, uint32_t ltop, TcHi<NTH>& h) {
+  uint32_t v[32];
+  h.carry = 0;
+  tc_ld32<NTH>(c, rw, 0, v);
+  tc_limbs8(v, h.carry, h.L);
+  h.cadd = h.L[0] > ltop ? 1u : 0u;
+}
+template <int NTH>
+PAI_DEV void tc_hi_tile(const TcCtx<NTH>& c, int rw, int j, const SOpnd& m, const Opnd& N, TcHi<NTH>& h, uint32_t out[8]) {
+  PAI_UNROLL
+  for (int i = 0; i < 7; i++) out[i] = h.L[i + 1];
+  if (j < NTH - 1) {
+    uint32_t v[32];
+    tc_ld32<NTH>(c, rw, 32 * (j + 1), v);
+    tc_limbs8(v, h.carry, h.L);
+    out[7] = h.L[0];
+  } else {
+    // byte columns 2D-4 .. 2D-2: products of the top three digits of m and n
+    const uint32_t mt = ld_quad(m, 2 * NTH - 1).w, nt = N.p[(2 * NTH - 1) * N.s].w;
+    const uint32_t m1 = (mt >> 8) & 0xffu, m2 = (mt >> 16) & 0xffu, m3 = mt >> 24;
+    const uint32_t n1 = (nt >> 8) & 0xffu, n2 = (nt >> 16) & 0xffu, n3 = nt >> 24;
+    const uint32_t e0 = m1 * n3 + m2 * n2 + m3 * n1, e1 = m2 * n3 + m3 * n2, e2 = m3 * n3;
+    out[7] = h.carry + e0 + (e1 << 8) + (e2 << 16);            // < 2^32: floor(m n / R) < R
+  }
+}
+
+// E2: t = (T_hi + [T_lo != 0]) + hi + [guard > ltop] -> park (in place); carry = [t >= n]; A <- (KL - m) mod R, wtop
+template <int NTH>
+PAI_FN void tc_epi_t(const TcCtx<NTH>* c, int rw, SOpnd A, Opnd Ag, Opnd P, const DigitEnv* dc, TcRow* st) {
+  constexpr int BL = NTH > 8 ? NTH / 2 : NTH;                   // park tiles loaded together (register budget)
+  uint32_t th[BL][8];
+  PAI_UNROLL
+  for (int j = 0; j < BL; j++) ld_tile(P, j, th[j]);             // park loads in flight before the first TMEM read
+  TcHi<NTH> h;
+  tc_hi_begin<NTH>(*c, rw, st->ltop, h);
+  uint32_t cy = h.cadd, bo = 0;
+  PAI_UNROLL
+  for (int j0 = 0; j0 < NTH; j0 += BL) {
+    if (j0 > 0) {
+      PAI_UNROLL
+      for (int j = 0; j < BL; j++) ld_tile(P, j0 + j, th[j]);
+    }
+    PAI_UNROLL
+    for (int jj = 0; jj < BL; jj++) {
+      const int j = j0 + jj;
+      uint32_t hi[8], t[8], nt[8], d[8];
+      tc_hi_tile<NTH>(*c, rw, j, A, dc->N, h, hi);
+      cy = add8c(t, th[jj], hi, cy);
+      st_tile(P, j, t);
+      ld_tile(dc->N, j, nt);
+      bo = sub8b(d, t, nt, bo);
+    }
+  }
+  st->carry = (cy != 0u) | (bo ^ 1u);
+  st->wtop = 1u - big_rsub<NTH>(Ag, dc->KL) + st->carry;
+}
+
+// P2 (multiplication): B = x0*y1 + x1*y0 + W;  B_lo -> A (over W), B_hi (+ wtop + [B_lo != 0]) -> bh
+template <int NTH, class XT>
+PAI_FN void tc_prod2_mul(SOpnd A, SOpnd bh, XT x0, XT x1, Opnd y0, Opnd y1, TcRow* st) {
+  Acc acc;
+  acc_clear(acc);
+  TcLow low; low.lowor = 0; low.top = 0;
+  uint32_t nz2 = 0;
+  for (int k = 0; k < 2 * NTH; k++) {
+    int lo = k - NTH + 1 > 0 ? k - NTH + 1 : 0;
+    int hi = k < NTH ? k : NTH - 1;
+    for (int i = lo; i <= hi; i++) {
+      uint32_t x[8], y[8];
+      ld_tile(x0, i, x); ld_tile(y1, k - i, y);
+      tile_mac(acc, x, y);
+      ld_tile(x1, i, x); ld_tile(y0, k - i, y);
+      tile_mac(acc, x, y);
+    }
+    uint32_t v[8];
+    if (k < NTH) {
+      uint32_t w[8];
+      ld_tile(A, k, w);
+      acc_add_low(acc, w);
+      acc_resolve_low(acc, v);
+      st_tile(A, k, v);
+      tc_low_tile(low, v, k == NTH - 1);
+      if (k == NTH - 1) { nz2 = (low.lowor | low.top) != 0u; st->ltop = ~low.top + (low.lowor == 0u ? 1u : 0u); }
+    } else {
+      if (k == NTH) acc.C[0] += st->wtop + nz2;
+      acc_resolve_low(acc, v);
+      st_tile(bh, k - NTH, v);
+    }
+    acc_shift8(acc);
+  }
+  st->ovf2 = lo32(acc.E[0]) + acc.C[0];
+}
+
+// P2 (squaring): B = 2*x0*x1 + W (all NTH^2 cross tiles once in S, doubled on the way in)
+template <int NTH>
+PAI_FN void tc_prod2_sqr(SOpnd A, SOpnd bh, SOpnd x0, SOpnd x1, TcRow* st) {
+  Acc acc, S;
+  acc_clear(acc);
+  acc_clear(S);
+  uint32_t topbit = 0, nz2 = 0;
+  TcLow low; low.lowor = 0; low.top = 0;
+  for (int k = 0; k < 2 * NTH; k++) {
+    int lo = k - NTH + 1 > 0 ? k - NTH + 1 : 0;
+    int hc = k < NTH ? k : NTH - 1;
+    for (int i = lo; i <= hc; i++) {
+      uint32_t x[8], y[8];
+      ld_tile(x0, i, x); ld_tile(x1, k - i, y);
+      tile_mac(S, x, y);
+    }
+    {
+      uint32_t d[8], d2[8];
+      acc_resolve_low(S, d);
+      acc_shift8(S);
+      d2[0] = (d[0] << 1) | topbit;
+      PAI_UNROLL
+      for (int j = 1; j < 8; j++) d2[j] = (d[j] << 1) | (d[j - 1] >> 31);
+      topbit = d[7] >> 31;
+      acc_add_low(acc, d2);
+    }
+    uint32_t v[8];
+    if (k < NTH) {
+      uint32_t w[8];
+      ld_tile(A, k, w);
+      acc_add_low(acc, w);
+      acc_resolve_low(acc, v);
+      st_tile(A, k, v);
+      tc_low_tile(low, v, k == NTH - 1);
+      if (k == NTH - 1) { nz2 = (low.lowor | low.top) != 0u; st->ltop = ~low.top + (low.lowor == 0u ? 1u : 0u); }
+    } else {
+      if (k == NTH) acc.C[0] += st->wtop + nz2;
+      acc_resolve_low(acc, v);
+      st_tile(bh, k - NTH, v);
+    }
+    acc_shift8(acc);
+  }
+  st->ovf2 = lo32(acc.E[0]) + acc.C[0] + topbit;
+}
+
+// E4: z = B_hi' + hi' + [guard > ltop] (+ ovf2 * R) < 3n + 3, reduced modulo n in place (bh)
+template <int NTH>
+PAI_FN void tc_epi_z(const TcCtx<NTH>* c, int rw, SOpnd A, SOpnd bh, Opnd bhg, const DigitEnv* dc, TcRow* st) {
+  TcHi<NTH> h;
+  tc_hi_begin<NTH>(*c, rw, st->ltop, h);
+  uint32_t cy = h.cadd, b1 = 0, b2 = 0, b3 = 0;
+  for (int j = 0; j < NTH; j++) {
+    uint32_t hi[8], th[8], t[8], nt[8], d[8];
+    tc_hi_tile<NTH>(*c, rw, j, A, dc->N, h, hi);
+    ld_tile(bh, j, th);
+    cy = add8c(t, th, hi, cy);
+    st_tile(bh, j, t);
+    ld_tile(dc->N, j, nt);   b1 = sub8b(d, t, nt, b1);
+    ld_tile(dc->N2, j, nt);  b2 = sub8b(d, t, nt, b2);
+    ld_tile(dc->N3, j, nt);  b3 = sub8b(d, t, nt, b3);
+  }
+  digit_reduce3<NTH>(bhg, *dc, st->ovf2 + cy, b1, b2, b3);
+}
+
+// Z0 = t - (n & mask): park -> shared half-buffer, all park loads issued together (one L2 round trip, not NTH)
+template <int NTH>
+PAI_FN void tc_z0_copy(SOpnd dst, Opnd P, Opnd N, uint32_t mask) {
+  constexpr int BL = NTH > 8 ? NTH / 2 : NTH;
+  uint32_t bo = 0;
+  PAI_UNROLL
+  for (int j0 = 0; j0 < NTH; j0 += BL) {
+    uint32_t t[BL][8];
+    PAI_UNROLL
+    for (int j = 0; j < BL; j++) ld_tile(P, j0 + j, t[j]);
+    PAI_UNROLL
+    for (int j = 0; j < BL; j++) {
+      uint32_t y[8], r[8];
+      ld_tile(N, j0 + j, y);
+      PAI_UNROLL
+      for (int i = 0; i < 8; i++) y[i] &= mask;
+      bo = sub8b(r, t[j], y, bo);
+      st_tile(dst, j0 + j, r);
+    }
+  }
+}
+
+// ---- one product, all phases.  Operand resolvers map a row to its operand (rows differ only in their base address):
+//   x0, x1: digits of the first factor (shared half-buffers, or generic operands for rows read straight from global
+//   memory); y0, y1: digits of the second factor (generic; ignored for SQR);  bhi: index of the half-buffer where Z1 is
+//   built (may be x0's: its tiles are dead when they are overwritten);  z0i: the half-buffer that receives Z0.
+template <int NTH, bool SQR, class FX0, class FX1, class FY0, class FY1>
+PAI_DEV void tc_op(TcCtx<NTH>& c, FX0 x0, FX1 x1, FY0 y0, FY1 y1, int bhi, int z0i) {
+  TcRow st[TC_RL];
+  TC_PROF_START(c, t0);
+  TC_EACH_ROW {
+    st[rw].nz = 0;
+    if constexpr (SQR) tc_prod1_sqr<NTH>(tc_as<NTH>(c, rw), tc_park<NTH>(c, rw), x0(rw), &st[rw]);
+    else tc_prod1_mul<NTH>(tc_as<NTH>(c, rw), tc_park<NTH>(c, rw), x0(rw), y0(rw), &st[rw]);
+  }
+  TC_PROF(c, t0, SQR ? 0 : 8);
+  tc_gemm<NTH>(c, 0);
+  TC_PROF(c, t0, 1);
+  TC_EACH_ROW tc_epi_m<NTH>(&c, rw, tc_as<NTH>(c, rw));
+  TC_PROF(c, t0, 2);
+  tc_gemm<NTH>(c, 1);
+  TC_PROF(c, t0, 3);
+  TC_EACH_ROW tc_epi_t<NTH>(&c, rw, tc_as<NTH>(c, rw), tc_a<NTH>(c, rw), tc_park<NTH>(c, rw), c.dc, &st[rw]);
+  TC_PROF(c, t0, 4);
+  TC_EACH_ROW {
+    if constexpr (SQR) tc_prod2_sqr<NTH>(tc_as<NTH>(c, rw), tc_hs<NTH>(c, bhi, rw), x0(rw), x1(rw), &st[rw]);
+    else tc_prod2_mul<NTH>(tc_as<NTH>(c, rw), tc_hs<NTH>(c, bhi, rw), x0(rw), x1(rw), y0(rw), y1(rw), &st[rw]);
+  }
+  TC_PROF(c, t0, SQR ? 5 : 9);
+  tc_gemm<NTH>(c, 0);
+  TC_PROF(c, t0, 1);
+  TC_EACH_ROW tc_epi_m<NTH>(&c, rw, tc_as<NTH>(c, rw));
+  TC_PROF(c, t0, 2);
+  tc_gemm<NTH>(c, 1);
+  TC_PROF(c, t0, 3);
+  TC_EACH_ROW tc_epi_z<NTH>(&c, rw, tc_as<NTH>(c, rw), tc_hs<NTH>(c, bhi, rw), tc_h<NTH>(c, bhi, rw), c.dc, &st[rw]);
+  TC_PROF(c, t0, 6);
+  TC_EACH_ROW tc_z0_copy<NTH>(tc_hs<NTH>(c, z0i, rw), tc_park<NTH>(c, rw), c.dc->N, 0u - st[rw].carry);
+  TC_PROF(c, t0, 7);
+#if !defined(PAI_HOSTSIM)
+  if (c.prof && (threadIdx.x & 31) == 0) c.prof[SQR ? 10 : 11] += 1;
+#endif
+}
+
+// in-place forms on the two shared half-buffers: x0 in H[a], x1 in H[1-a]  ->  Z1 in H[a], Z0 in H[1-a]; the caller flips a
+template <int NTH>
+PAI_DEV void tc_sqr_inplace(TcCtx<NTH>& c, int a) {
+  auto X = [&](int rw) { return tc_hs<NTH>(c, a, rw); };
+  auto Y = [&](int rw) { return tc_hs<NTH>(c, a ^ 1, rw); };
+  auto G = [&](int rw) { return tc_h<NTH>(c, a, rw); };
+  tc_op<NTH, true>(c, X, Y, G, G, a, a ^ 1);
+}
+template <int NTH, class FY0, class FY1>
+PAI_DEV void tc_mul_inplace(TcCtx<NTH>& c, int a, FY0 y0, FY1 y1) {
+  auto X = [&](int rw) { return tc_hs<NTH>(c, a, rw); };
+  auto Y = [&](int rw) { return tc_hs<NTH>(c, a ^ 1, rw); };
+  tc_op<NTH, false>(c, X, Y, y0, y1, a, a ^ 1);
+}
+template <int NTH>
+PAI_DEV void tc_tbl_store(TcCtx<NTH>& c, int e, int a) {          // T[e] = (H[a], H[1-a])
+  TC_EACH_ROW {
+    big_copy<NTH>(tc_tbl<NTH>(c, e, 0, rw), tc_h<NTH>(c, a, rw));
+    big_copy<NTH>(tc_tbl<NTH>(c, e, 1, rw), tc_h<NTH>(c, a ^ 1, rw));
+  }
+}
+template <int NTH>
+PAI_DEV void tc_tbl_load(TcCtx<NTH>& c, int e, int a) {           // (H[a], H[1-a]) = T[e]
+  TC_EACH_ROW {
+    big_copy<NTH>(tc_h<NTH>(c, a, rw), tc_tbl<NTH>(c, e, 0, rw));
+    big_copy<NTH>(tc_h<NTH>(c, a ^ 1, rw), tc_tbl<NTH>(c, e, 1, rw));
+  }
+}
+
+// Sliding-window exponentiation with the host-built program (see dpow_prog): base in (H[a], H[1-a]); returns the new a.
+template <int NTH>
+PAI_DEV int tc_pow_prog(TcCtx<NTH>& c, int a, const uint32_t* prog, int nops, int nodd) {
+  tc_tbl_store<NTH>(c, 0, a);                                             // T[0] = base
+  if (nodd > 1) {
+    tc_sqr_inplace<NTH>(c, a); a ^= 1;
+    tc_tbl_store<NTH>(c, nodd, a);                                        // base^2
+    tc_tbl_load<NTH>(c, 0, a);
+    for (int k = 1; k < nodd; k++) {                                      // T[k] = T[k-1] * base^2
+      tc_mul_inplace<NTH>(c, a, [&](int rw) { return tc_tbl<NTH>(c, nodd, 0, rw); }, [&](int rw) { return tc_tbl<NTH>(c, nodd, 1, rw); });
+      a ^= 1;
+      tc_tbl_store<NTH>(c, k, a);
+    }
+  }
+  tc_tbl_load<NTH>(c, (int)(prog[0] & 0xffffu), a);
+  for (int i = 1; i < nops; i++) {
+    const uint32_t op = prog[i];
+    const int nsq = (int)(op >> 16), idx = (int)(op & 0xffffu);
+    for (int s = 0; s < nsq; s++) { tc_sqr_inplace<NTH>(c, a); a ^= 1; }
+    if (idx != 0xffff) {
+      tc_mul_inplace<NTH>(c, a, [&](int rw) { return tc_tbl<NTH>(c, idx, 0, rw); }, [&](int rw) { return tc_tbl<NTH>(c, idx, 1, rw); });
+      a ^= 1;
+    }
+  }
+  return a;
+}
+
+// raw_encrypt (phe/paillier.py:102-139) for the rows of one group: c = (1 + n*m) * r^n mod n^2.
+//   rows: global row index of every row of the group (clamped to batch - 1), store: whether it is a real row.
+template <int NTH>
+PAI_DEV void tc_encrypt_rows(TcCtx<NTH>& c, const uint32_t* prog, int nops, int nodd, const uint32_t* m, const uint32_t* r,
+                             uint32_t* out, const long* g, const bool* store) {
+  const DigitEnv& dc = *c.dc;
+  const int ln = 8 * NTH, lc = 16 * NTH;
+  // (r, 0) * RR: enter the Montgomery domain; Z1 -> H[0], Z0 -> H[1]
+  tc_op<NTH, false>(
+      c, [&](int rw) { Opnd o; o.p = (u4*)(r + g[rw] * ln); o.s = 1; return o; }, [&](int) { return dc.ZERO; },
+      [&](int) { return dc.RR.d0; }, [&](int) { return dc.RR.d1; }, 0, 1);
+  int a = 1;
+  if (nops <= 0) {                                                        // exponent 0 -> Montgomery one
+    TC_EACH_ROW { big_copy<NTH>(tc_h<NTH>(c, a, rw), dc.ONEM.d0); big_copy<NTH>(tc_h<NTH>(c, a ^ 1, rw), dc.ONEM.d1); }
+  } else {
+    a = tc_pow_prog<NTH>(c, a, prog, nops, nodd);
+  }
+  // times the PLAIN digit pair (1, m) of the nude ciphertext 1 + n*m: leaves the domain
+  tc_mul_inplace<NTH>(c, a, [&](int) { return dc.ONE; }, [&](int rw) { Opnd o; o.p = (u4*)(m + g[rw] * ln); o.s = 1; return o; });
+  a ^= 1;
+  TC_EACH_ROW {
+    DNum z; z.d0 = tc_h<NTH>(c, a, rw); z.d1 = tc_h<NTH>(c, a ^ 1, rw);
+    Opnd o;
+    if (store[rw]) { o.p = (u4*)(out + g[rw] * lc); o.s = 1; }
+    else o = tc_tbl<NTH>(c, 0, 0, rw);                                   // scratch: table entry 0 (2*NTH tiles)
+    digits_to_plain<NTH>(o, z, dc.N);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// raw_decrypt with CRT (phe/paillier.py:328-374) on the tensor-core path: the same program as prog_decrypt_digit
+// (pai_digit.cuh), every product modulo p^2 / q^2 through tc_op.  Fixed windows of W bits (secret exponent shared by
+// the batch: no digit is skipped); the 2^W-entry table lives in global memory, entry 2^W is the park slot.
+template <int NTP, int W>
+PAI_DEV int tc_pow_fixed(TcCtx<NTP>& c, int a, const uint32_t* e, int nl, int nwin) {
+  const DigitEnv& dc = *c.dc;
+  TC_EACH_ROW { big_copy<NTP>(tc_tbl<NTP>(c, 0, 0, rw), dc.ONEM.d0); big_copy<NTP>(tc_tbl<NTP>(c, 0, 1, rw), dc.ONEM.d1); }
+  tc_tbl_store<NTP>(c, 1, a);
+  tc_sqr_inplace<NTP>(c, a); a ^= 1;
+  tc_tbl_store<NTP>(c, 2, a);
+  for (int i = 3; i < (1 << W); i++) {
+    tc_mul_inplace<NTP>(c, a, [&](int rw) { return tc_tbl<NTP>(c, 1, 0, rw); }, [&](int rw) { return tc_tbl<NTP>(c, 1, 1, rw); });
+    a ^= 1;
+    tc_tbl_store<NTP>(c, i, a);
+  }
+  tc_tbl_load<NTP>(c, (int)exp_digit(e, nl, (nwin - 1) * W, W), a);
+  for (int wi = nwin - 2; wi >= 0; wi--) {
+    for (int s = 0; s < W; s++) { tc_sqr_inplace<NTP>(c, a); a ^= 1; }
+    const int d = (int)exp_digit(e, nl, wi * W, W);
+    tc_mul_inplace<NTP>(c, a, [&](int rw) { return tc_tbl<NTP>(c, d, 0, rw); }, [&](int rw) { return tc_tbl<NTP>(c, d, 1, rw); });
+    a ^= 1;
+  }
+  return a;
+}
+
+// one prime side: m_x = L(c^(x-1) mod x^2) * h mod x  -> returns the index of the half-buffer that holds it (NTP tiles)
+template <int NTP, int W>
+PAI_DEV int tc_decrypt_half(TcCtx<NTP>& c, DSideC<NTP>& S, const uint8_t* bands, const uint32_t* cbase, const long* g) {
+  DigitEnv& dc = S.dc;
+  c.dc = &dc;
+  c.band[0] = bands;
+  c.band[1] = bands + tc_band_bytes(NTP);
+  const int lc = 32 * NTP;
+  const DNum Ek[4] = {dc.RR, dc.E3, dc.E4, dc.E5};
+  // X = c * R mod x^2 from the four NTP-tile pieces of c (accumulated in table entry 0)
+  for (int i = 0; i < 4; i++) {
+    tc_op<NTP, false>(
+        c, [&](int rw) { Opnd o; o.p = (u4*)(cbase + g[rw] * lc + (size_t)i * 8 * NTP); o.s = 1; return o; }, [&](int) { return dc.ZERO; },
+        [&](int) { return Ek[i].d0; }, [&](int) { return Ek[i].d1; }, 0, 1);
+    if (i == 0) tc_tbl_store<NTP>(c, 0, 1);
+    else TC_EACH_ROW {
+      DNum acc, add;
+      acc.d0 = tc_tbl<NTP>(c, 0, 0, rw); acc.d1 = tc_tbl<NTP>(c, 0, 1, rw);
+      add.d0 = tc_h<NTP>(c, 1, rw); add.d1 = tc_h<NTP>(c, 0, rw);
+      dadd<NTP>(acc, add, dc.N);
+    }
+  }
+  int a = 0;
+  tc_tbl_load<NTP>(c, 0, a);
+  if (S.nwin <= 0) {
+    TC_EACH_ROW { big_copy<NTP>(tc_h<NTP>(c, a, rw), dc.ONEM.d0); big_copy<NTP>(tc_h<NTP>(c, a ^ 1, rw), dc.ONEM.d1); }
+  } else {
+    a = tc_pow_fixed<NTP, W>(c, a, S.e, 8 * NTP, S.nwin);
+  }
+  tc_mul_inplace<NTP>(c, a, [&](int) { return dc.ONE; }, [&](int) { return dc.ZERO; });       // plain digits u = u0 + x*u1
+  a ^= 1;
+  TC_EACH_ROW {
+    Opnd u0 = tc_h<NTP>(c, a, rw), u1 = tc_h<NTP>(c, a ^ 1, rw);
+    // L(u) = (u-1)//x = u1 if u0 >= 1;  u0 == 0: u1 - 1, and -1 = x - 1 (mod x) if u1 == 0   (pai_digit.cuh)
+    uint32_t u0z = big_is_zero<NTP>(u0);
+    uint32_t u1z = big_is_zero<NTP>(u1);
+    big_sub_masked<NTP>(u1, u1, dc.ONE, 0u - (u0z & (u1z ^ 1u)));
+    const uint32_t sel = u0z & u1z;
+    for (int t = 0; t < NTP; t++) {
+      uint32_t l[8], n[8];
+      ld_tile(u1, t, l); ld_tile(dc.N, t, n);
+      if (t == 0) n[0] -= 1u;
+      PAI_UNROLL
+      for (int i = 0; i < 8; i++) l[i] = sel ? n[i] : l[i];
+      st_tile(u1, t, l);
+    }
+    mont_mul<NTP>(u0, u1, S.hM, dc.N, dc.NI);                              // L * h mod x  (over u0's buffer)
+  }
+  return a;
+}
+
+template <int NTP, int W>
+PAI_DEV void tc_decrypt_rows(TcCtx<NTP>& c, DSideC<NTP>& P, DSideC<NTP>& Qs, const Opnd& pinvqM, const uint8_t* bands,
+                             const uint32_t* cbase, uint32_t* out, const long* g, const bool* store) {
+  const int ln = 16 * NTP;
+  int ip = tc_decrypt_half<NTP, W>(c, P, bands, cbase, g);
+  TC_EACH_ROW { if (store[rw]) store_row(out + g[rw] * ln, tc_h<NTP>(c, ip, rw), 2 * NTP); }     // m_p -> low half of the row
+  int iq = tc_decrypt_half<NTP, W>(c, Qs, bands + 2 * tc_band_bytes(NTP), cbase, g);
+  TC_EACH_ROW {
+    uint32_t* out_row = out + g[rw] * ln;
+    Opnd mq = tc_h<NTP>(c, iq, rw), mp = tc_h<NTP>(c, iq ^ 1, rw), uo = tc_a<NTP>(c, rw);
+    if (store[rw]) load_row(mp, out_row, 2 * NTP, 2 * NTP);
+    else big_copy<NTP>(mp, mq);
+    // u = (m_q - m_p) * p^-1 mod q     (m_p < p < q, m_q < q)
+    uint32_t bo = big_sub_masked<NTP>(mq, mq, mp, 0xffffffffu);
+    big_add_masked<NTP>(mq, mq, Qs.dc.N, 0u - bo);
+    mont_mul<NTP>(uo, mq, pinvqM, Qs.dc.N, Qs.dc.NI);
+    // m = m_p + u * p : the product goes straight to the output row (a scratch table entry for padding rows)
+    Opnd o;
+    if (store[rw]) { o.p = (u4*)out_row; o.s = 1; }
+    else o = tc_tbl<NTP>(c, 0, 0, rw);
+    big_mul<NTP, NTP, 2 * NTP>(o, uo, P.dc.N, 0u);
+    uint32_t cy = 0;
+    for (int t = 0; t < 2 * NTP; t++) {
+      uint32_t x[8], b[8], r[8];
+      ld_tile(o, t, x);
+      if (t < NTP) ld_tile(mp, t, b);
+      else { PAI_UNROLL for (int i = 0; i < 8; i++) b[i] = 0; }
+      cy = add8c(r, x, b, cy);
+      st_tile(o, t, r);
+    }
+  }
+}
+
+}  // namespace pai

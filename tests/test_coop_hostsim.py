@@ -86,11 +86,14 @@ def test_generic_powmod_through_the_warp_path(pkg, sim, monkeypatch):
 
 def test_tail_of_a_batch_goes_to_the_warp_path(pkg, sim, monkeypatch):
     """Whole waves on the throughput kernel, the remainder on the warp kernels, one call (the simulation build has
-    waves of 4 ciphertexts): results are in order and equal to the all-throughput run."""
+    waves of a few ciphertexts, pai_pub_wave): results are in order and equal to the all-throughput run."""
     fx = load_golden("vectors_256.json")
     n, p, q = H(fx["n"]), H(fx["p"]), H(fx["q"])
     rng = random.Random(3)
-    for batch in (5, 7, 8, 11):
+    probe = pkg.PublicContext(n, engine=sim)
+    wave = probe.wave()
+    probe.close()
+    for batch in (wave + 1, wave + 3, 2 * wave, 2 * wave + 3):
         ms = [rng.randrange(n) for _ in range(batch)]
         rs = [rng.randrange(1, n) for _ in range(batch)]
         outs = []
@@ -103,5 +106,5 @@ def test_tail_of_a_batch_goes_to_the_warp_path(pkg, sim, monkeypatch):
             outs.append((cs, priv.raw_decrypt(cs), launches))
             pub.close(); priv.close()
         assert outs[0][:2] == outs[1][:2] and outs[0][1] == ms
-        # 0 < batch % 4 <= 3 -> two launches more than the plain run (constants of the warp layout) or at least one
-        assert (outs[1][2] > outs[0][2]) == (batch % 4 != 0)
+        # 0 < batch % wave <= 3 -> two launches more than the plain run (constants of the warp layout) or at least one
+        assert (outs[1][2] > outs[0][2]) == (batch % wave != 0)
