@@ -65,32 +65,41 @@ def sliding_counts(e, w):
     return nsq, nmul
 
 
-def executed_macs(kb, n=None, scalar_bits=64):
-    """32x32->64 MACs the kernels really issue per op on the base-n digit path (pai_digit.cuh), counted from the loops:
-    dsqr<T> = T(T+1)/2 + 3 T^2 tile products, dmul<T> = 5 T^2, a tile product = 64 MACs, plus 2T truncated quotient
-    products (mul_lo8, 36 MACs) per dsqr/dmul; mont_mul<T> = 2 T^2 + T tiles + T mul_lo8; big_mul T x T = T^2 tiles.
-    2048-bit: dsqr<8> = 228 tiles + 16 mul_lo8, dmul<8> = 320 + 16."""
-    def dsqr(t):
-        return 64 * (t * (t + 1) // 2 + 3 * t * t) + 36 * 2 * t
-
-    def dmul(t):
-        return 64 * 5 * t * t + 36 * 2 * t
-
+def executed_macs(kb, n=None, scalar_bits=64, enc_path="digit", dec_path="digit"):
+    """32x32->64 MACs the kernels really issue on the INTEGER pipe per op, counted from the loops.
+    digit family (pai_digit.cuh): dsqr<T> = T(T+1)/2 + 3 T^2 tile products, dmul<T> = 5 T^2, a tile product = 64 MACs,
+    plus 2T truncated quotient products (mul_lo8, 36 MACs) per dsqr/dmul (2048-bit: 228 + 16 and 320 + 16).
+    tc family (pai_tc.cuh): the reductions run on the tensor cores, what is left is dsqr = T(T+1)/2 + T^2 (100 at 2048 bit),
+    dmul = 3 T^2 (192), no quotient products; `tensor` counts the u8 x u8 MACs of the four [128 x D] x [D x D] GEMMs
+    per product and ciphertext.  mont_mul<T> = 2 T^2 + T tiles + T mul_lo8; big_mul T x T = T^2 tiles."""
     def mont(t):
         return 64 * (2 * t * t + t) + 36 * t
+
+    def ops(t, path):
+        if path == "tc":
+            return 64 * (t * (t + 1) // 2 + t * t), 64 * 3 * t * t, 4 * (32 * t) ** 2
+        return 64 * (t * (t + 1) // 2 + 3 * t * t) + 36 * 2 * t, 64 * 5 * t * t + 36 * 2 * t, 0
     th = kb // 256                       # tiles of n
     tp = kb // 512                       # tiles of p, q
     if n is None:
         n = (1 << kb) - 1
     nsq, nmul = sliding_counts(n, 6)
-    enc = (nsq + 1) * dsqr(th) + (nmul + 31 + 2) * dmul(th) + 64 * th * th          # table: 1 sqr + 31 mul; entry, exit; Z0 + n Z1
+    dsqr, dmul, tens = ops(th, enc_path)
+    n_sq, n_mul = nsq + 1, nmul + 31 + 2                                         # table: 1 sqr + 31 mul; entry, exit
+    enc = n_sq * dsqr + n_mul * dmul + 64 * th * th                              # + Z0 + n Z1
+    enc_tensor = (n_sq + n_mul) * tens
     nwin = -(-(kb // 2) // 5)
-    side = 4 * dmul(tp) + dsqr(tp) + 29 * dmul(tp) + (nwin - 1) * (5 * dsqr(tp) + dmul(tp)) + dmul(tp) + mont(tp)
+    dsq, dmu, tens_d = ops(tp, dec_path)
+    s_sq, s_mul = 1 + 5 * (nwin - 1), 4 + 29 + (nwin - 1) + 1
+    side = s_sq * dsq + s_mul * dmu + mont(tp)
     dec = 2 * side + mont(tp) + 64 * tp * tp
+    dec_tensor = 2 * (s_sq + s_mul) * tens_d
     add = 2 * mont(2 * th)
     nw = -(-scalar_bits // 4)
-    mul = 2 * dmul(th) + dsqr(th) + 13 * dmul(th) + (nw - 1) * (4 * dsqr(th) + dmul(th)) + dmul(th) + 64 * th * th
-    return {"encrypt": enc, "decrypt": dec, "add": add, "mul": mul, "mont_full": mont(2 * th)}
+    dsqr_i, dmul_i, _ = ops(th, "digit")
+    mul = 2 * dmul_i + dsqr_i + 13 * dmul_i + (nw - 1) * (4 * dsqr_i + dmul_i) + dmul_i + 64 * th * th
+    return {"encrypt": enc, "decrypt": dec, "add": add, "mul": mul, "mont_full": mont(2 * th),
+            "encrypt_tensor_u8_macs": enc_tensor, "decrypt_tensor_u8_macs": dec_tensor}
 
 
 def canonical_macs(kb, scalar_bits=64):
@@ -548,7 +557,8 @@ def leg_headline(dev, args, pb, np, key, pool):
                                                            "decrypt": Bp / (t2 - t1) / e2e["decrypts_per_s"]}}
         del ml, rl, cl, dl
     res = {"enc_ms": enc_ms, "dec_ms": dec_ms, "t_wall": t_wall, "launches": launches, "clocks": clocks, "e2e": e2e,
-           "e2e_python": e2e_py, "parity": parity, "ln": ln, "lc": lc, "wave_enc": pub.wave(), "wave_dec": priv.wave()}
+           "e2e_python": e2e_py, "parity": parity, "ln": ln, "lc": lc, "wave_enc": pub.wave(), "wave_dec": priv.wave(),
+           "enc_path": pub.kernel_path(), "dec_path": priv.kernel_path()}
     return res, (pub, priv, d_m, d_r, d_c, d_d)
 
 
@@ -677,10 +687,11 @@ def leg_3072(dev, args, pb, np, pool, peak_mac_s, H, load_golden):
            "encrypts_per_s": total / (enc_ms * 1e-3), "decrypts_per_s": total / (dec_ms * 1e-3), "enc_ms": enc_ms, "dec_ms": dec_ms,
            "key_broadcast_ms": bcast_ms if dev.world > 1 else None, "steps": 1,
            "note": "one timed pass over the whole vector after a one-wave warm-up; inputs uniform in [1, n) (pai_random_lt_n)"}
-    ex, ca = executed_macs(3072, n), canonical_macs(3072)
+    ex, ca = executed_macs(3072, n, enc_path=pub.kernel_path(), dec_path=priv.kernel_path()), canonical_macs(3072)
+    out["kernel_family"] = {"encrypt": pub.kernel_path(), "decrypt": priv.kernel_path()}
     per_gpu_enc = total / dev.world / (enc_ms * 1e-3)
     per_gpu_dec = total / dev.world / (dec_ms * 1e-3)
-    out["roofline"] = {"bound": "int_pipe", "kernel": "k_body<EncDigitBody<12>>", "frac": per_gpu_enc * ex["encrypt"] / peak_mac_s,
+    out["roofline"] = {"bound": "int_pipe", "kernel": "k_body<TcEncBody<12>>" if pub.kernel_path() == "tc" else "k_body<EncDigitBody<12>>", "frac": per_gpu_enc * ex["encrypt"] / peak_mac_s,
                        "canonical_frac": per_gpu_enc * ca["encrypt"] / peak_mac_s, "executed_macs_per_encrypt": ex["encrypt"],
                        "decrypt": {"frac": per_gpu_dec * ex["decrypt"] / peak_mac_s, "canonical_frac": per_gpu_dec * ca["decrypt"] / peak_mac_s}}
     if dev.rank == 0 and pool is not None:
@@ -941,18 +952,23 @@ def main():
             dev.dist.destroy_process_group()
         return
 
-    ex, ca = executed_macs(KEY_BITS, key[0]), canonical_macs(KEY_BITS)
+    ex, ca = executed_macs(KEY_BITS, key[0], enc_path=head["enc_path"], dec_path=head["dec_path"]), canonical_macs(KEY_BITS)
     hbm_peak, hbm_src = _hbm_peak()
     ach = enc_per_s / world * ex["encrypt"]
+    kern = {"tc": "k_body<TcEncBody<8>> (raw_encrypt: digit products on the integer pipe, Montgomery reductions as tcgen05 kind::i8 GEMMs)",
+            "digit": "k_body<EncDigitBody<8>> (raw_encrypt, r^n mod n^2 on base-n digits)", "full": "k_body<EncBody<16>>"}
+    kern_d = {"tc": "k_body<TcDecBody<4,5>>", "digit": "k_body<DecDigitBody<4,5>>", "full": "k_body<DecBody<4,5>>"}
+    tensor_peak = 2 * json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"] / 2 if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
     roofline = {
-        "bound": "int_pipe", "kernel": "k_body<EncDigitBody<8>> (raw_encrypt, r^n mod n^2 on base-n digits)",
+        "bound": "int_pipe", "kernel": kern[head["enc_path"]], "kernel_family": head["enc_path"],
         "achieved": ach / 1e12, "peak": peak_mac_s / 1e12, "unit": "TMAC/s (32x32->64 MACs the kernel executes, per GPU)",
         "frac": ach / peak_mac_s,
         "frac_of_nominal_pipe": ach / nominal_mac_s, "peak_nominal": nominal_mac_s / 1e12,
         "canonical_frac": enc_per_s / world * ca["encrypt"] / peak_mac_s,
         "executed_macs_per_encrypt": ex["encrypt"], "canonical_macs_per_encrypt": ca["encrypt"],
-        "note": "frac = executed MACs / measured IMAD.WIDE.U32 peak.  canonical_frac uses SURVEY 8(d)'s schoolbook count, which the "
-                "base-n digit arithmetic halves (algorithmic saving, not throughput) -- it may exceed 1.  peak_nominal = 32 MAC/clk/SM "
+        "note": "frac = MACs executed on the integer pipe / measured IMAD.WIDE.U32 peak.  canonical_frac uses SURVEY 8(d)'s schoolbook count; the "
+                "base-n digit arithmetic halves it and the tensor-core reductions halve it again (algorithmic savings, not throughput) -- "
+                "it exceeds 1.  peak_nominal = 32 MAC/clk/SM "
                 "(half-rate fmaheavy instruction); the measured peak is ~25: an IMAD.WIDE with a 64-bit addend issues every 5th cycle "
                 "per SM sub-partition, not every 4th (bench_micro/imad_peak: the same instruction without an addend, "
                 "mul_wide_no_addend, is reported beside it), so ~0.78 of nominal is the ceiling of this instruction and ncu's "
@@ -960,8 +976,12 @@ def main():
         "peak_source": "measured IMAD.WIDE.U32.X rate %.1f MAC/clk/SM (%s) x 148 SMs x %.0f MHz (SM clock sampled under load)"
                        % (pk_mac, peak.get("source"), sm_mhz),
         "peak_micro": peak,
-        "decrypt": {"kernel": "k_body<DecDigitBody<4,5>>", "frac": dec_per_s / world * ex["decrypt"] / peak_mac_s,
+        "decrypt": {"kernel": kern_d[head["dec_path"]], "kernel_family": head["dec_path"], "frac": dec_per_s / world * ex["decrypt"] / peak_mac_s,
                     "canonical_frac": dec_per_s / world * ca["decrypt"] / peak_mac_s, "executed_macs_per_decrypt": ex["decrypt"]},
+        "tensor": {"u8_macs_per_encrypt": ex["encrypt_tensor_u8_macs"], "achieved_tmacs": enc_per_s / world * ex["encrypt_tensor_u8_macs"] / 1e12,
+                   "peak_tmacs_int8_dense": tensor_peak, "frac": enc_per_s / world * ex["encrypt_tensor_u8_macs"] / 1e12 / tensor_peak,
+                   "note": "the reductions' GEMMs ([128 x D] x Toeplitz, u8 x u8 -> s32); peak = measured dense bf16 TFLOP/s x 2 (int8) / 2 (MAC = 2 ops); "
+                           "the tensor pipe is a helper here, not the bound"},
         "hbm": {"achieved_gbs": enc_per_s / world * (ln * 2 + lc) * 4 / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,
                 "frac": enc_per_s / world * (ln * 2 + lc) * 4 / 1e9 / hbm_peak},
         "traffic": _ncu_traffic("encrypt"),

@@ -26,8 +26,9 @@
  *   - Batch size needs no tuning: pai_encrypt / pai_decrypt / pai_mod_powmod_shared route a batch (or the remainder of
  *     a batch beyond whole waves of the thread-per-ciphertext kernels) of up to 0.3 wave to warp-per-ciphertext
  *     kernels with ~10x lower latency.  Environment switches, read at call time / context creation:
- *     PAI_COOP_MAX=<rows> (0 = never use the warp kernels), PAI_ENCRYPT_PATH=full, PAI_DECRYPT_PATH=full (full-width
- *     Montgomery kernels instead of the base-n digit kernels).  All variants return identical bits.
+ *     PAI_COOP_MAX=<rows> (0 = never use the warp kernels), PAI_TC=0 (base-n digit kernels on the integer pipe instead of
+ *     the tensor-core reductions), PAI_ENCRYPT_PATH=full, PAI_DECRYPT_PATH=full (full-width Montgomery kernels instead of
+ *     the base-n digit kernels).  All variants return identical bits.
  */
 #ifndef PAILLIER_B200_H
 #define PAILLIER_B200_H
@@ -82,6 +83,11 @@ int pai_pub_c_limbs(const pai_pub* k);     /* 2*Ln: limbs of ciphertexts        
  * nothing; host code that pipelines a long vector in chunks sizes the chunks with it).  No reference counterpart:
  * the reference processes one element per call (examples/federated_learning_with_encryption.py:122-133). */
 long pai_pub_wave(pai_pub* k);
+/* kernel family that serves pai_encrypt for this key: 0 = full-width Montgomery, 1 = base-n digit arithmetic on the
+ * integer pipe (pai_digit.cuh), 2 = base-n digits with both multiplications of every Montgomery reduction on the
+ * tensor cores (pai_tc.cuh; keys up to 3072 bits).  All families return identical bits; PAI_TC=0 / PAI_ENCRYPT_PATH=full
+ * at context creation select the lower ones.  Instrumentation only (bench.py reports the MACs of the active family). */
+int pai_pub_kernel_path(const pai_pub* k);
 
 /* c[i] = (1 + n*m[i]) * r[i]^n mod n^2        raw_encrypt, phe/paillier.py:102-139
  * (= obfuscate of the nude ciphertext, :603-624).  Any m, r < 2^(32 Ln) is accepted and reduced. */
@@ -105,6 +111,7 @@ int pai_priv_destroy(pai_priv* k);
 int pai_priv_n_limbs(const pai_priv* k);
 int pai_priv_c_limbs(const pai_priv* k);
 long pai_priv_wave(pai_priv* k);            /* as pai_pub_wave, for the decrypt kernel */
+int pai_priv_kernel_path(const pai_priv* k);   /* as pai_pub_kernel_path (tensor-core family: keys up to 4096 bits) */
 /* copies of the derived constants (host buffers of pai_priv_n_limbs() limbs each; NULL = skip):
  * p, q (ordered), p_inverse, hp, hq -- for the drop-in key object's attributes */
 int pai_priv_get(const pai_priv* k, uint32_t* p, uint32_t* q, uint32_t* p_inverse, uint32_t* hp, uint32_t* hq);

@@ -135,71 +135,69 @@ PAI_DEV void cta_encrypt_digit(u4* smem, const CtaId& id, const uint32_t* prog, 
   }
 }
 
-// ---- encrypt with the reductions on the tensor cores (pai_tc.cuh).  Shared memory map:
-//   [ compact encrypt constants | pad | band(N') | band(n) | H0 | H1 | A (one per 128-thread group) ]
+// ---- kernels with the reductions on the tensor cores (pai_tc.cuh).  Shared memory map of all of them:
+//   [ constants | pad | bands (2 per digit modulus) | H0 | H1 | A (one per 128-thread group) ]
 // H0/H1: the two half-buffers of every thread (interleaved, stride nthr); A: the groups' MMA operand buffers.
 template <int NTH>
-PAI_HD size_t tc_enc_smem_bytes(int nthr) {
+PAI_HD size_t tc_smem_bytes(int const_limbs, int nbands, int nthr) {
   const int groups = nthr >= TC_M ? nthr / TC_M : 1;
-  return (size_t)dc_enc_limbs(NTH) * 4 + 256 + 2 * (size_t)tc_band_bytes(NTH) + 2 * (size_t)(2 * NTH) * nthr * 16 +
+  return (size_t)const_limbs * 4 + 256 + (size_t)nbands * tc_band_bytes(NTH) + 2 * (size_t)(2 * NTH) * nthr * 16 +
          (size_t)groups * TC_M * 32 * NTH;
 }
+template <int NTH>
+PAI_HD size_t tc_enc_smem_bytes(int nthr) { return tc_smem_bytes<NTH>(dc_enc_limbs(NTH), 2, nthr); }
+template <int NTH>
+PAI_HD size_t tc_pow_smem_bytes(int nthr) { return tc_smem_bytes<NTH>(dc_pow_limbs(NTH), 2, nthr); }
+template <int NTP>
+PAI_HD size_t tc_dec_smem_bytes(int nthr) { return tc_smem_bytes<NTP>((2 * (dside_limbs<NTP>() / 4) + 2 * NTP) * 4, 4, nthr); }
 template <int NTH>
 #if !defined(PAI_HOSTSIM)
 __host__ __device__
 #endif
 constexpr int tc_tmem_cols(int groups) { int need = groups * 32 * NTH, c = 32; while (c < need && c < 512) c *= 2; return c; }
 
+// Set-up shared by the tensor-core kernels: copies the bands to shared memory, allocates TMEM and the groups' mbarriers,
+// fills in the context of the calling thread.  Returns the shared-memory address of the bands.  `entries`: table entries
+// per thread including the park slot.
 template <int NTH>
-PAI_DEV void cta_encrypt_tc(u4* smem, const CtaId& id, const uint32_t* prog, int nops, int nodd, const uint32_t* m, const uint32_t* r,
-                            uint32_t* out, long batch, u4* tbl, const uint32_t* gzero, const uint8_t* gbands, int stagger_cycles,
-                            long long* prof = nullptr) {
+PAI_DEV uint8_t* tc_cta_begin(TcCtx<NTH>& c, u4* smem, const CtaId& id, int const_limbs, int nbands, const uint8_t* gbands, u4* tbl,
+                              int entries, int stagger_cycles) {
   const int D = 32 * NTH;
-  DigitEnv dc;
-  digit_bind_enc<NTH>(dc, smem, gzero);
   uint8_t* base = (uint8_t*)smem;
-  size_t off = (size_t)dc_enc_limbs(NTH) * 4;
+  size_t off = (size_t)const_limbs * 4;
 #if !defined(PAI_HOSTSIM)
   off += (128u - ((tc_smem_u32(base) + (uint32_t)off) & 127u)) & 127u;     // operands of the MMA: 128-byte aligned
 #else
   off = (off + 127) & ~(size_t)127;
 #endif
-  uint8_t* band1 = base + off;
-  uint8_t* band2 = band1 + tc_band_bytes(NTH);
-  u4* H0 = (u4*)(band2 + tc_band_bytes(NTH));
+  uint8_t* bands = base + off;
+  u4* H0 = (u4*)(bands + (size_t)nbands * tc_band_bytes(NTH));
   u4* H1 = H0 + (size_t)(2 * NTH) * id.nthr;
   uint8_t* A0 = (uint8_t*)(H1 + (size_t)(2 * NTH) * id.nthr);
-  TcCtx<NTH> c;
-  c.dc = &dc;
   c.H[0] = H0; c.H[1] = H1;
-  c.band[0] = band1; c.band[1] = band2;
-  c.slots = nodd + 1;
+  c.band[0] = bands; c.band[1] = bands + tc_band_bytes(NTH);
+  c.slots = entries - 1;
   c.nthr = id.nthr;
-  const int ln = 8 * NTH;
-  (void)ln; (void)D;
+  const size_t tbl_cta = (size_t)entries * 4 * NTH * id.nthr;
+  (void)D;
 #if defined(PAI_HOSTSIM)
   // one call walks the TC_RL rows of the CTA (id.nthr == TC_RL); they sit in different 8-row groups of the operand
-  // layout from CTA to CTA so that the (row / 8) part of the addressing is exercised too
-  for (int i = 0; i < 2 * tc_band_bytes(NTH); i++) band1[i] = gbands[i];
+  // layout from CTA to CTA so that the (row / 8) and (row % 8) parts of the addressing are exercised too
+  for (int i = 0; i < nbands * tc_band_bytes(NTH); i++) bands[i] = gbands[i];
   c.A = (u4*)A0;
   c.tid = 0;
   c.row0 = 8 * (id.cta % 16) + (TC_RL < 8 ? TC_RL * ((id.cta / 2) % (8 / TC_RL)) : 0);
-  c.tbl.p = tbl + (size_t)id.cta * ((size_t)(nodd + 2) * 4 * NTH * id.nthr);
+  c.tbl.p = tbl + (size_t)id.cta * tbl_cta;
   c.tbl.s = id.nthr;
   (void)stagger_cycles;
-  for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
-    long g[TC_RL]; bool store[TC_RL];
-    TC_EACH_ROW { g[rw] = chunk * id.nthr + rw; store[rw] = g[rw] < batch; if (!store[rw]) g[rw] = batch - 1; }
-    tc_encrypt_rows<NTH>(c, prog, nops, nodd, m, r, out, g, store);
-  }
 #else
   __shared__ uint64_t s_mbar[2];
   __shared__ uint32_t s_tmem;
   const int groups = id.nthr / TC_M;
   {
     const u4* src = (const u4*)gbands;
-    u4* dst = (u4*)band1;
-    for (int i = id.tid; i < 2 * tc_band_bytes(NTH) / 16; i += id.nthr) dst[i] = src[i];
+    u4* dst = (u4*)bands;
+    for (int i = id.tid; i < nbands * tc_band_bytes(NTH) / 16; i += id.nthr) dst[i] = src[i];
   }
   if (id.tid == 0) { tc_mbar_init(&s_mbar[0], 1); tc_mbar_init(&s_mbar[1], 1); }
   if (id.tid < 32) {
@@ -219,123 +217,111 @@ PAI_DEV void cta_encrypt_tc(u4* smem, const CtaId& id, const uint32_t* prog, int
   c.tmem = s_tmem + (uint32_t)(grp * D);
   c.mbar = &s_mbar[grp];
   c.phase = 0;
-  c.tbl.p = tbl + (size_t)id.cta * ((size_t)(nodd + 2) * 4 * NTH * id.nthr) + id.tid;
+  c.prof = nullptr;
+  c.tbl.p = tbl + (size_t)id.cta * tbl_cta + id.tid;
   c.tbl.s = id.nthr;
-  c.prof = prof ? prof + ((size_t)id.cta * (id.nthr / 32) + id.tid / 32) * 16 : nullptr;
   if (grp == 1 && stagger_cycles > 0) {                // put the groups out of phase: one multiplies while the other reduces
     const long long t0 = clock64();
     while (clock64() - t0 < (long long)stagger_cycles) {}
   }
-  for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
-    long g = chunk * id.nthr + id.tid;
-    bool store = g < batch;
-    if (!store) g = batch - 1;
-    tc_encrypt_rows<NTH>(c, prog, nops, nodd, m, r, out, &g, &store);
-  }
+#endif
+  return bands;
+}
+template <int NTH>
+PAI_DEV void tc_cta_end(const TcCtx<NTH>& c, const CtaId& id) {
+#if !defined(PAI_HOSTSIM)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (id.tid < 32) {
-    if (groups == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(tc_tmem_cols<NTH>(2)));
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(tc_tmem_cols<NTH>(1)));
+    const uint32_t t0 = c.tmem - (uint32_t)(c.grp * 32 * NTH);
+    if (id.nthr / TC_M == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(t0), "n"(tc_tmem_cols<NTH>(2)));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(t0), "n"(tc_tmem_cols<NTH>(1)));
   }
+#else
+  (void)c; (void)id;
 #endif
+}
+// rows of this thread (simulation: of the TC_RL rows of the CTA) in chunk `chunk`
+PAI_DEV void tc_chunk_rows(const CtaId& id, const TcCtx<2>*, long chunk, long batch, long* g, bool* store) {
+  TC_EACH_ROW {
+    g[rw] = chunk * id.nthr + id.tid + rw;
+    store[rw] = g[rw] < batch;
+    if (!store[rw]) g[rw] = batch - 1;
+  }
+}
+
+template <int NTH>
+PAI_DEV void cta_encrypt_tc(u4* smem, const CtaId& id, const uint32_t* prog, int nops, int nodd, const uint32_t* m, const uint32_t* r,
+                            uint32_t* out, long batch, u4* tbl, const uint32_t* gzero, const uint8_t* gbands, int stagger_cycles,
+                            long long* prof = nullptr) {
+  DigitEnv dc;
+  digit_bind_enc<NTH>(dc, smem, gzero);
+  TcCtx<NTH> c;
+  c.dc = &dc;
+  tc_cta_begin<NTH>(c, smem, id, dc_enc_limbs(NTH), 2, gbands, tbl, nodd + 2, stagger_cycles);
+#if !defined(PAI_HOSTSIM)
+  c.prof = prof ? prof + ((size_t)id.cta * (id.nthr / 32) + id.tid / 32) * 16 : nullptr;
+#else
+  (void)prof;
+#endif
+  for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
+    long g[TC_RL]; bool store[TC_RL];
+    tc_chunk_rows(id, nullptr, chunk, batch, g, store);
+    tc_encrypt_rows<NTH>(c, prog, nops, nodd, m, r, out, g, store);
+  }
+  tc_cta_end<NTH>(c, id);
+}
+
+// ---- c^k mod n^2 (raw_mul) on the tensor-core path.  consts = compact constants with ONEM and E3 (dc_pow_limbs); the
+// window count is made uniform over the 128-thread group (the groups are independent of each other).
+template <int NTH, int W>
+PAI_DEV void cta_powmod_tc(u4* smem, const CtaId& id, const uint32_t* base, const uint32_t* exp, int exp_limbs, uint32_t* out, long batch,
+                           u4* tbl, const uint32_t* gzero, const uint8_t* gbands, int stagger_cycles) {
+  DigitEnv dc;
+  digit_bind_pow<NTH>(dc, smem, gzero);
+  TcCtx<NTH> c;
+  c.dc = &dc;
+  tc_cta_begin<NTH>(c, smem, id, dc_pow_limbs(NTH), 2, gbands, tbl, (1 << W) + 1, stagger_cycles);
+#if !defined(PAI_HOSTSIM)
+  __shared__ int s_nwin[2];
+#endif
+  for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
+    long g[TC_RL]; bool store[TC_RL];
+    tc_chunk_rows(id, nullptr, chunk, batch, g, store);
+    int nwin = 0;
+    TC_EACH_ROW { int w = (limbs_bitlen(exp + g[rw] * exp_limbs, exp_limbs) + W - 1) / W; nwin = w > nwin ? w : nwin; }
+#if !defined(PAI_HOSTSIM)
+    if (c.row0 == 0) s_nwin[c.grp] = 0;
+    tc_bar_sync(1 + c.grp, TC_M);
+    nwin = __reduce_max_sync(0xffffffffu, nwin);
+    if ((id.tid & 31) == 0) atomicMax(&s_nwin[c.grp], nwin);
+    tc_bar_sync(1 + c.grp, TC_M);
+    nwin = s_nwin[c.grp];
+    tc_bar_sync(1 + c.grp, TC_M);
+#endif
+    tc_powmod_rows<NTH, W>(c, base, exp, exp_limbs, nwin, out, g, store);
+  }
+  tc_cta_end<NTH>(c, id);
 }
 
 // ---- decrypt with the reductions on the tensor cores.  consts = [ P side | Q side | pinvqM ] as in cta_decrypt_digit;
-// shared memory map: [ consts | pad | bands of p (2) | bands of q (2) | H0 | H1 | A per group ]
-template <int NTP>
-PAI_HD size_t tc_dec_smem_bytes(int nthr) {
-  const int groups = nthr >= TC_M ? nthr / TC_M : 1;
-  return (size_t)(2 * (dside_limbs<NTP>() / 4) + 2 * NTP) * 16 + 256 + 4 * (size_t)tc_band_bytes(NTP) + 2 * (size_t)(2 * NTP) * nthr * 16 +
-         (size_t)groups * TC_M * 32 * NTP;
-}
+// bands: p (2), q (2)
 template <int NTP, int W>
 PAI_DEV void cta_decrypt_tc(u4* smem, const CtaId& id, int nwin_p, int nwin_q, const uint32_t* cin, uint32_t* out, long batch, u4* tbl,
                             const uint8_t* gbands, int stagger_cycles) {
-  const int D = 32 * NTP;
   DSideC<NTP> P, Qs;
   dside_bind<NTP>(P, smem, nwin_p);
   dside_bind<NTP>(Qs, smem + dside_limbs<NTP>() / 4, nwin_q);
   Opnd pinvqM{smem + 2 * (dside_limbs<NTP>() / 4), 1};
-  uint8_t* base = (uint8_t*)smem;
-  size_t off = (size_t)(2 * (dside_limbs<NTP>() / 4) + 2 * NTP) * 16;
-#if !defined(PAI_HOSTSIM)
-  off += (128u - ((tc_smem_u32(base) + (uint32_t)off) & 127u)) & 127u;
-#else
-  off = (off + 127) & ~(size_t)127;
-#endif
-  uint8_t* bands = base + off;
-  u4* H0 = (u4*)(bands + 4 * tc_band_bytes(NTP));
-  u4* H1 = H0 + (size_t)(2 * NTP) * id.nthr;
-  uint8_t* A0 = (uint8_t*)(H1 + (size_t)(2 * NTP) * id.nthr);
   TcCtx<NTP> c;
   c.dc = &P.dc;
-  c.H[0] = H0; c.H[1] = H1;
-  c.band[0] = bands; c.band[1] = bands + tc_band_bytes(NTP);
-  c.slots = 1 << W;
-  c.nthr = id.nthr;
-  (void)D;
-  const size_t tbl_cta = (size_t)((1 << W) + 1) * 4 * NTP * id.nthr;
-#if defined(PAI_HOSTSIM)
-  for (int i = 0; i < 4 * tc_band_bytes(NTP); i++) bands[i] = gbands[i];
-  c.A = (u4*)A0;
-  c.tid = 0;
-  c.row0 = 8 * (id.cta % 16) + (TC_RL < 8 ? TC_RL * ((id.cta / 2) % (8 / TC_RL)) : 0);
-  c.tbl.p = tbl + (size_t)id.cta * tbl_cta;
-  c.tbl.s = id.nthr;
-  (void)stagger_cycles;
+  uint8_t* bands = tc_cta_begin<NTP>(c, smem, id, (2 * (dside_limbs<NTP>() / 4) + 2 * NTP) * 4, 4, gbands, tbl, (1 << W) + 1, stagger_cycles);
   for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
     long g[TC_RL]; bool store[TC_RL];
-    TC_EACH_ROW { g[rw] = chunk * id.nthr + rw; store[rw] = g[rw] < batch; if (!store[rw]) g[rw] = batch - 1; }
+    tc_chunk_rows(id, nullptr, chunk, batch, g, store);
     tc_decrypt_rows<NTP, W>(c, P, Qs, pinvqM, bands, cin, out, g, store);
   }
-#else
-  __shared__ uint64_t s_mbar[2];
-  __shared__ uint32_t s_tmem;
-  const int groups = id.nthr / TC_M;
-  {
-    const u4* src = (const u4*)gbands;
-    u4* dst = (u4*)bands;
-    for (int i = id.tid; i < 4 * tc_band_bytes(NTP) / 16; i += id.nthr) dst[i] = src[i];
-  }
-  if (id.tid == 0) { tc_mbar_init(&s_mbar[0], 1); tc_mbar_init(&s_mbar[1], 1); }
-  if (id.tid < 32) {
-    if (groups == 2) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&s_tmem)), "n"(tc_tmem_cols<NTP>(2)));
-    else asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&s_tmem)), "n"(tc_tmem_cols<NTP>(1)));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const int grp = id.tid / TC_M;
-  c.grp = grp;
-  c.A = (u4*)(A0 + (size_t)grp * TC_M * D);
-  c.tid = id.tid;
-  c.row0 = id.tid % TC_M;
-  c.tmem = s_tmem + (uint32_t)(grp * D);
-  c.mbar = &s_mbar[grp];
-  c.phase = 0;
-  c.tbl.p = tbl + (size_t)id.cta * tbl_cta + id.tid;
-  c.tbl.s = id.nthr;
-  c.prof = nullptr;
-  if (grp == 1 && stagger_cycles > 0) {
-    const long long t0 = clock64();
-    while (clock64() - t0 < (long long)stagger_cycles) {}
-  }
-  for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
-    long g = chunk * id.nthr + id.tid;
-    bool store = g < batch;
-    if (!store) g = batch - 1;
-    tc_decrypt_rows<NTP, W>(c, P, Qs, pinvqM, bands, cin, out, &g, &store);
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (id.tid < 32) {
-    if (groups == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(tc_tmem_cols<NTP>(2)));
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(tc_tmem_cols<NTP>(1)));
-  }
-#endif
+  tc_cta_end<NTP>(c, id);
 }
 
 // ---- mulmod.  consts = [ blob ]

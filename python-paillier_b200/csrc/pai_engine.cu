@@ -67,6 +67,13 @@ struct TcEncBody {
   const uint32_t* gzero; const uint8_t* bands; int stagger; long long* prof;
   PAI_MEM void run(u4* smem, const CtaId& id) const { cta_encrypt_tc<NTH>(smem, id, prog, nops, nodd, m, r, out, batch, tbl, gzero, bands, stagger, prof); }
 };
+template <int NTH, int W>
+struct TcPowBody {
+  const uint32_t* consts; int const_quads;
+  const uint32_t* base; const uint32_t* exp; int exp_limbs; uint32_t* out; long batch; u4* tbl; const uint32_t* gzero;
+  const uint8_t* bands; int stagger;
+  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_powmod_tc<NTH, W>(smem, id, base, exp, exp_limbs, out, batch, tbl, gzero, bands, stagger); }
+};
 template <int NTP, int W>
 struct TcDecBody {
   const uint32_t* consts; int const_quads;
@@ -666,6 +673,19 @@ int do_encrypt_tc(pai_pub* k, const uint32_t* m_, const uint32_t* r, uint32_t* c
   return rt_launch_group(body, g.grid, g.nthr, g.smem, s);
 }
 template <int NTH>
+int do_powmod_tc(pai_pub* k, const uint32_t* base, const uint32_t* d_exp, int exp_limbs, uint32_t* out, long batch, rt_stream s) {
+  typedef TcPowBody<NTH, W_VAR> B;
+  pai_mod* m = k->nmod;
+  Geom g;
+  int rc = tc_geometry_of<B, NTH>(m->device, [](int nthr) { return tc_pow_smem_bytes<NTH>(nthr); }, batch, g);
+  if (rc) return rc;
+  rc = m->ws.get(s).tbl.ensure((size_t)g.grid * (((size_t)1 << W_VAR) + 1) * 4 * NTH * g.nthr * 16);
+  if (rc) return rc;
+  B body{k->d_enc_consts, dc_pow_limbs(NTH) / 4, base, d_exp, exp_limbs, out, batch, (u4*)m->ws.get(s).tbl.p,
+         m->d_blob + dc_zero_offset(NTH), k->d_tc, k->tc_stagger};
+  return rt_launch_group(body, g.grid, g.nthr, g.smem, s);
+}
+template <int NTH>
 long encrypt_wave_tc(pai_pub* k) {
   Geom g;
   if (tc_geometry<NTH>(k, 1L << 40, g)) return 0;
@@ -1196,6 +1216,7 @@ int pai_pub_destroy(pai_pub* k) {
 }
 int pai_pub_n_limbs(const pai_pub* k) { return k ? k->ln : PAI_E_ARG; }
 int pai_pub_c_limbs(const pai_pub* k) { return k ? 2 * k->ln : PAI_E_ARG; }
+int pai_pub_kernel_path(const pai_pub* k) { return !k ? PAI_E_ARG : (k->use_tc ? 2 : (k->use_digit ? 1 : 0)); }
 long pai_pub_wave(pai_pub* k) {
   DeviceGuard device_guard_; (void)device_guard_;
   if (!k) return PAI_E_ARG;
@@ -1310,6 +1331,10 @@ int pai_raw_mul(pai_pub* k, const uint32_t* d_a, const uint32_t* d_s, uint32_t* 
   DISPATCH_NT(m->NT, rc = do_invert<NT>(m, d_a, lc / 8, flag, (uint32_t*)w.w_base.p, status, batch, s));
   if (rc) return rc;
   // 3. base ^ exponent mod n^2
+  if (k->use_tc) {
+    DISPATCH_TC(k->nmod->NT, rc = do_powmod_tc<NTH>(k, (const uint32_t*)w.w_base.p, (const uint32_t*)w.w_exp.p, ln, d_c, batch, s));
+    return rc;
+  }
   if (k->use_digit) {
     DISPATCH_NTH(k->nmod->NT, rc = do_powmod_digit<NTH>(k, (const uint32_t*)w.w_base.p, (const uint32_t*)w.w_exp.p, ln, d_c, batch, s));
     return rc;
@@ -1378,6 +1403,7 @@ int pai_priv_destroy(pai_priv* k) {
 }
 int pai_priv_n_limbs(const pai_priv* k) { return k ? 16 * k->NTP : PAI_E_ARG; }
 int pai_priv_c_limbs(const pai_priv* k) { return k ? 32 * k->NTP : PAI_E_ARG; }
+int pai_priv_kernel_path(const pai_priv* k) { return !k ? PAI_E_ARG : (k->use_tc ? 2 : (k->use_digit ? 1 : 0)); }
 long pai_priv_wave(pai_priv* k) {
   DeviceGuard device_guard_; (void)device_guard_;
   if (!k) return PAI_E_ARG;

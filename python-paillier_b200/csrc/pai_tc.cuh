@@ -35,7 +35,7 @@
 namespace pai {
 
 #if defined(PAI_HOSTSIM)
-constexpr int TC_RL = 4;                  // rows of a group the simulation walks (placed in varying 8-row groups of the layout)
+constexpr int TC_RL = 2;                  // rows of a group the simulation walks (placed in varying 8-row groups of the layout)
 #else
 constexpr int TC_RL = 1;                  // the GPU thread owns one row; state lives in registers
 #endif
@@ -200,11 +200,16 @@ PAI_DEV void tc_gemm(TcCtx<NTH>& c, int which) {
   TC_EACH_ROW {
     const int r = c.row0 + rw;
     for (int j = 0; j < D; j++) {
-      int64_t sum = 0;
+      uint32_t sum = 0;                                   // <= D * 255^2 < 2^24
       for (int kap = 0; kap < NTH; kap++) {
         const int u0 = D - 32 - 32 * kap;
-        for (int kp = 0; kp < 32; kp++)
-          sum += (int64_t)a[tc_a_off(D, r, 32 * kap + kp)] * c.band[which][tc_band_off(u0 + j, kp)];
+        for (int h = 0; h < 2; h++) {                     // 16 contiguous digits of the row x 16 contiguous band bytes
+          const uint8_t* pa = a + tc_a_off(D, r, 32 * kap + 16 * h);
+          const uint8_t* pb = c.band[which] + tc_band_off(u0 + j, 16 * h);
+          uint32_t s16 = 0;
+          for (int t = 0; t < 16; t++) s16 += (uint32_t)pa[t] * pb[t];
+          sum += s16;
+        }
       }
       c.tmem[rw][j] = (int32_t)sum;
     }
@@ -685,8 +690,8 @@ PAI_DEV void tc_encrypt_rows(TcCtx<NTH>& c, const uint32_t* prog, int nops, int 
 // raw_decrypt with CRT (phe/paillier.py:328-374) on the tensor-core path: the same program as prog_decrypt_digit
 // (pai_digit.cuh), every product modulo p^2 / q^2 through tc_op.  Fixed windows of W bits (secret exponent shared by
 // the batch: no digit is skipped); the 2^W-entry table lives in global memory, entry 2^W is the park slot.
-template <int NTP, int W>
-PAI_DEV int tc_pow_fixed(TcCtx<NTP>& c, int a, const uint32_t* e, int nl, int nwin) {
+template <int NTP, int W, class FD>
+PAI_DEV int tc_pow_fixed_f(TcCtx<NTP>& c, int a, FD digit, int nwin) {          // digit(rw, window index) -> table entry of row rw
   const DigitEnv& dc = *c.dc;
   TC_EACH_ROW { big_copy<NTP>(tc_tbl<NTP>(c, 0, 0, rw), dc.ONEM.d0); big_copy<NTP>(tc_tbl<NTP>(c, 0, 1, rw), dc.ONEM.d1); }
   tc_tbl_store<NTP>(c, 1, a);
@@ -697,14 +702,60 @@ PAI_DEV int tc_pow_fixed(TcCtx<NTP>& c, int a, const uint32_t* e, int nl, int nw
     a ^= 1;
     tc_tbl_store<NTP>(c, i, a);
   }
-  tc_tbl_load<NTP>(c, (int)exp_digit(e, nl, (nwin - 1) * W, W), a);
+  TC_EACH_ROW {
+    const int d = digit(rw, nwin - 1);
+    big_copy<NTP>(tc_h<NTP>(c, a, rw), tc_tbl<NTP>(c, d, 0, rw));
+    big_copy<NTP>(tc_h<NTP>(c, a ^ 1, rw), tc_tbl<NTP>(c, d, 1, rw));
+  }
   for (int wi = nwin - 2; wi >= 0; wi--) {
     for (int s = 0; s < W; s++) { tc_sqr_inplace<NTP>(c, a); a ^= 1; }
-    const int d = (int)exp_digit(e, nl, wi * W, W);
-    tc_mul_inplace<NTP>(c, a, [&](int rw) { return tc_tbl<NTP>(c, d, 0, rw); }, [&](int rw) { return tc_tbl<NTP>(c, d, 1, rw); });
+    tc_mul_inplace<NTP>(c, a, [&](int rw) { return tc_tbl<NTP>(c, digit(rw, wi), 0, rw); },
+                        [&](int rw) { return tc_tbl<NTP>(c, digit(rw, wi), 1, rw); });
     a ^= 1;
   }
   return a;
+}
+template <int NTP, int W>
+PAI_DEV int tc_pow_fixed(TcCtx<NTP>& c, int a, const uint32_t* e, int nl, int nwin) {
+  return tc_pow_fixed_f<NTP, W>(c, a, [&](int, int wi) { return (int)exp_digit(e, nl, wi * W, W); }, nwin);
+}
+
+// c^k mod n^2 with per-element exponents (EncryptedNumber._raw_mul, phe/paillier.py:749-751) -- prog_powmod_digit on
+// the tensor-core path.  base rows: plain ciphertexts (2*NTH tiles = c_0 + c_1*R); nwin is uniform over the group.
+template <int NTH, int W>
+PAI_DEV void tc_powmod_rows(TcCtx<NTH>& c, const uint32_t* base, const uint32_t* exp, int nl, int nwin, uint32_t* out,
+                            const long* g, const bool* store) {
+  const DigitEnv& dc = *c.dc;
+  const int lc = 16 * NTH;
+  for (int i = 0; i < 2; i++) {                                           // (c_0, 0) * R^2 + (c_1, 0) * R^3
+    const DNum E = i == 0 ? dc.RR : dc.E3;
+    tc_op<NTH, false>(
+        c, [&](int rw) { Opnd o; o.p = (u4*)(base + g[rw] * lc + (size_t)i * 8 * NTH); o.s = 1; return o; }, [&](int) { return dc.ZERO; },
+        [&](int) { return E.d0; }, [&](int) { return E.d1; }, 0, 1);
+    if (i == 0) tc_tbl_store<NTH>(c, 0, 1);
+    else TC_EACH_ROW {
+      DNum acc, add;
+      acc.d0 = tc_tbl<NTH>(c, 0, 0, rw); acc.d1 = tc_tbl<NTH>(c, 0, 1, rw);
+      add.d0 = tc_h<NTH>(c, 1, rw); add.d1 = tc_h<NTH>(c, 0, rw);
+      dadd<NTH>(acc, add, dc.N);
+    }
+  }
+  int a = 0;
+  tc_tbl_load<NTH>(c, 0, a);
+  if (nwin <= 0) {
+    TC_EACH_ROW { big_copy<NTH>(tc_h<NTH>(c, a, rw), dc.ONEM.d0); big_copy<NTH>(tc_h<NTH>(c, a ^ 1, rw), dc.ONEM.d1); }
+  } else {
+    a = tc_pow_fixed_f<NTH, W>(c, a, [&](int rw, int wi) { return (int)exp_digit(exp + g[rw] * nl, nl, wi * W, W); }, nwin);
+  }
+  tc_mul_inplace<NTH>(c, a, [&](int) { return dc.ONE; }, [&](int) { return dc.ZERO; });
+  a ^= 1;
+  TC_EACH_ROW {
+    DNum z; z.d0 = tc_h<NTH>(c, a, rw); z.d1 = tc_h<NTH>(c, a ^ 1, rw);
+    Opnd o;
+    if (store[rw]) { o.p = (u4*)(out + g[rw] * lc); o.s = 1; }
+    else o = tc_tbl<NTH>(c, 0, 0, rw);
+    digits_to_plain<NTH>(o, z, dc.N);
+  }
 }
 
 // one prime side: m_x = L(c^(x-1) mod x^2) * h mod x  -> returns the index of the half-buffer that holds it (NTP tiles)

@@ -53,6 +53,8 @@ SYMBOLS = {
     "pai_pub_c_limbs": (ctypes.c_int, [_vp]),
     "pai_pub_wave": (ctypes.c_long, [_vp]),
     "pai_priv_wave": (ctypes.c_long, [_vp]),
+    "pai_pub_kernel_path": (ctypes.c_int, [_vp]),
+    "pai_priv_kernel_path": (ctypes.c_int, [_vp]),
     "pai_encrypt": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_long, _vp]),
     "pai_random_lt_n": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_ulonglong, _vp, ctypes.c_long, _vp]),
     "pai_decimal_width": (ctypes.c_int, [ctypes.c_int]),
@@ -388,6 +390,10 @@ class PublicContext:
         """Rows per full wave of the throughput encrypt kernel (batches that are multiples of it waste nothing)."""
         return int(self.eng.lib.pai_pub_wave(self.h))
 
+    def kernel_path(self):
+        """"full" | "digit" | "tc": the kernel family behind encrypt_dev for this key (include/paillier_b200.h)."""
+        return ("full", "digit", "tc")[int(self.eng.lib.pai_pub_kernel_path(self.h))]
+
     def raw_add(self, a, b):
         return limbs_to_ints(self.raw_add_host(ints_to_limbs(a, self.c_limbs), ints_to_limbs(b, self.c_limbs)))
 
@@ -453,3 +459,6 @@ class PrivateContext:
     def wave(self):
         """Rows per full wave of the throughput decrypt kernel."""
         return int(self.eng.lib.pai_priv_wave(self.h))
+
+    def kernel_path(self):
+        return ("full", "digit", "tc")[int(self.eng.lib.pai_priv_kernel_path(self.h))]

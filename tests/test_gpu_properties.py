@@ -198,26 +198,30 @@ def test_streams_and_cuda_graph(pkg, cuda_engine, gmp):
 
 
 def test_all_kernel_paths_agree(pkg, cuda_engine, monkeypatch):
-    """The base-n digit kernels (default), the full-width Montgomery kernels (PAI_*_PATH=full) and the
-    warp-per-ciphertext kernels (small batches, pai_coop.cuh) must give identical bits."""
+    """The tensor-core reduction kernels (default, pai_tc.cuh), the base-n digit kernels on the integer pipe (PAI_TC=0),
+    the full-width Montgomery kernels (PAI_*_PATH=full) and the warp-per-ciphertext kernels (small batches, pai_coop.cuh)
+    must give identical bits."""
     n, p, q = _key(1024)
     rng = random.Random(21)
     m = [rng.randrange(n) for _ in range(300)] + [0, 1, n - 1]
     r = [rng.randrange(1, n) for _ in m]
     k = [rng.getrandbits(64) for _ in m[:150]] + [n - 1 - rng.getrandbits(40) for _ in m[150:]]
     results = []
-    for env in ({"PAI_COOP_MAX": "0"}, {"PAI_ENCRYPT_PATH": "full", "PAI_DECRYPT_PATH": "full", "PAI_COOP_MAX": "0"},
-                {"PAI_COOP_MAX": "100000"}):
-        for key in ("PAI_ENCRYPT_PATH", "PAI_DECRYPT_PATH", "PAI_COOP_MAX"):
+    paths = []
+    for env in ({"PAI_COOP_MAX": "0"}, {"PAI_TC": "0", "PAI_COOP_MAX": "0"},
+                {"PAI_ENCRYPT_PATH": "full", "PAI_DECRYPT_PATH": "full", "PAI_COOP_MAX": "0"}, {"PAI_COOP_MAX": "100000"}):
+        for key in ("PAI_ENCRYPT_PATH", "PAI_DECRYPT_PATH", "PAI_COOP_MAX", "PAI_TC"):
             monkeypatch.delenv(key, raising=False)
         for key, val in env.items():
             monkeypatch.setenv(key, val)
         pub, priv = pkg.PublicContext(n), pkg.PrivateContext(p, q)       # the switches are read at context creation
+        paths.append((pub.kernel_path(), priv.kernel_path()))
         c = pub.raw_encrypt(m, r)
         t, st = pub.raw_mul(c, k)
         results.append((c, priv.raw_decrypt(c), t, st, priv.raw_decrypt(t)))
         pub.close(); priv.close()
-    assert results[0] == results[1] == results[2]
+    assert paths[:3] == [("tc", "tc"), ("digit", "digit"), ("full", "full")]
+    assert results[0] == results[1] == results[2] == results[3]
     assert results[0][1] == m
 
 
