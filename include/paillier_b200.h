@@ -103,6 +103,21 @@ int pai_raw_add(pai_pub* k, const uint32_t* d_a, const uint32_t* d_b, uint32_t* 
  *                                             _raw_mul, phe/paillier.py:721-751 */
 int pai_raw_mul(pai_pub* k, const uint32_t* d_a, const uint32_t* d_s, uint32_t* d_c, int32_t* d_status, long batch, void* stream);
 
+/* out = c[0] * c[1] * ... * c[batch-1] mod n^2 (one row): the homomorphic SUM of a whole ciphertext vector in two
+ * launches -- every thread multiplies its share of the rows in the Montgomery domain (entered once), the CTAs fold
+ * their threads' partial products in shared memory, a second launch folds the CTAs'.  The reference's idiom is
+ * sum(list_of_EncryptedNumber) / np.mean(...) = batch-1 sequential _raw_add calls (phe/tests/math_test.py:44-58,
+ * phe/paillier.py:705-719).  batch >= 1. */
+int pai_raw_sum(pai_pub* k, const uint32_t* d_c, long batch, uint32_t* d_out, void* stream);
+
+/* out = prod_i a[i]^s[i] mod n^2 (one row): the encrypted DOT PRODUCT of a ciphertext vector with plaintext scalars
+ * 0 <= s[i] < n, with _raw_mul's negative-scalar branch per element (d_status as in pai_raw_mul; may be NULL).  On the
+ * tensor-core kernel family the powers are taken by Straus' simultaneous exponentiation (one squaring chain shared by
+ * the group of elements a thread owns), then pai_raw_sum's reduction folds the groups.  The reference's idiom is
+ * sum(w_i * x_i) over EncryptedNumbers = one _raw_mul and one _raw_add per element
+ * (examples/logistic_regression_encrypted_model.py:170-180, phe/tests/math_test.py:50-58).  batch >= 1. */
+int pai_raw_dot(pai_pub* k, const uint32_t* d_a, const uint32_t* d_s, uint32_t* d_out, int32_t* d_status, long batch, void* stream);
+
 /* ---- private key: PaillierPrivateKey (phe/paillier.py:197-380) ---------------------------------
  * p, q: `limbs` limbs each, p*q = n.  Ordered internally so that p < q (:224-229).  All derived
  * constants (p^2, q^2, p^-1 mod q, hp, hq; :230-235) are computed by the engine on the device. */

@@ -242,7 +242,7 @@ PAI_DEV void tc_cta_end(const TcCtx<NTH>& c, const CtaId& id) {
 #endif
 }
 // rows of this thread (simulation: of the TC_RL rows of the CTA) in chunk `chunk`
-PAI_DEV void tc_chunk_rows(const CtaId& id, const TcCtx<2>*, long chunk, long batch, long* g, bool* store) {
+PAI_DEV void tc_chunk_rows(const CtaId& id, long chunk, long batch, long* g, bool* store) {
   TC_EACH_ROW {
     g[rw] = chunk * id.nthr + id.tid + rw;
     store[rw] = g[rw] < batch;
@@ -266,7 +266,7 @@ PAI_DEV void cta_encrypt_tc(u4* smem, const CtaId& id, const uint32_t* prog, int
 #endif
   for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
     long g[TC_RL]; bool store[TC_RL];
-    tc_chunk_rows(id, nullptr, chunk, batch, g, store);
+    tc_chunk_rows(id, chunk, batch, g, store);
     tc_encrypt_rows<NTH>(c, prog, nops, nodd, m, r, out, g, store);
   }
   tc_cta_end<NTH>(c, id);
@@ -287,7 +287,7 @@ PAI_DEV void cta_powmod_tc(u4* smem, const CtaId& id, const uint32_t* base, cons
 #endif
   for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
     long g[TC_RL]; bool store[TC_RL];
-    tc_chunk_rows(id, nullptr, chunk, batch, g, store);
+    tc_chunk_rows(id, chunk, batch, g, store);
     int nwin = 0;
     TC_EACH_ROW { int w = (limbs_bitlen(exp + g[rw] * exp_limbs, exp_limbs) + W - 1) / W; nwin = w > nwin ? w : nwin; }
 #if !defined(PAI_HOSTSIM)
@@ -300,6 +300,45 @@ PAI_DEV void cta_powmod_tc(u4* smem, const CtaId& id, const uint32_t* base, cons
     tc_bar_sync(1 + c.grp, TC_M);
 #endif
     tc_powmod_rows<NTH, W>(c, base, exp, exp_limbs, nwin, out, g, store);
+  }
+  tc_cta_end<NTH>(c, id);
+}
+
+// ---- prod_i c_i^(k_i) over groups of gsz elements per thread (Straus, tc_straus_rows): one output row per group.
+template <int NTH, int W>
+PAI_DEV void cta_straus_tc(u4* smem, const CtaId& id, const uint32_t* base, const uint32_t* exp, int exp_limbs, int gsz, uint32_t* out,
+                           long batch, u4* tbl, const uint32_t* gzero, const uint8_t* gbands, int stagger_cycles) {
+  DigitEnv dc;
+  digit_bind_pow<NTH>(dc, smem, gzero);
+  TcCtx<NTH> c;
+  c.dc = &dc;
+  tc_cta_begin<NTH>(c, smem, id, dc_pow_limbs(NTH), 2, gbands, tbl, (gsz << W) + 2, stagger_cycles);
+  const long ngroups = (batch + gsz - 1) / gsz;
+#if !defined(PAI_HOSTSIM)
+  __shared__ int s_nwin[2];
+#endif
+  for (long chunk = id.cta; chunk * id.nthr < ngroups; chunk += id.ncta) {
+    long g[TC_RL]; bool store[TC_RL];
+    tc_chunk_rows(id, chunk, ngroups, g, store);
+    int nwin = 0;
+    TC_EACH_ROW {
+      for (int i = 0; i < gsz; i++) {
+        long j = g[rw] * gsz + i;
+        if (j >= batch) break;
+        int w = (limbs_bitlen(exp + j * exp_limbs, exp_limbs) + W - 1) / W;
+        nwin = w > nwin ? w : nwin;
+      }
+    }
+#if !defined(PAI_HOSTSIM)
+    if (c.row0 == 0) s_nwin[c.grp] = 0;
+    tc_bar_sync(1 + c.grp, TC_M);
+    nwin = __reduce_max_sync(0xffffffffu, nwin);
+    if ((id.tid & 31) == 0) atomicMax(&s_nwin[c.grp], nwin);
+    tc_bar_sync(1 + c.grp, TC_M);
+    nwin = s_nwin[c.grp];
+    tc_bar_sync(1 + c.grp, TC_M);
+#endif
+    tc_straus_rows<NTH, W>(c, base, exp, exp_limbs, gsz, nwin, batch, out, g, store);
   }
   tc_cta_end<NTH>(c, id);
 }
@@ -318,7 +357,7 @@ PAI_DEV void cta_decrypt_tc(u4* smem, const CtaId& id, int nwin_p, int nwin_q, c
   uint8_t* bands = tc_cta_begin<NTP>(c, smem, id, (2 * (dside_limbs<NTP>() / 4) + 2 * NTP) * 4, 4, gbands, tbl, (1 << W) + 1, stagger_cycles);
   for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
     long g[TC_RL]; bool store[TC_RL];
-    tc_chunk_rows(id, nullptr, chunk, batch, g, store);
+    tc_chunk_rows(id, chunk, batch, g, store);
     tc_decrypt_rows<NTP, W>(c, P, Qs, pinvqM, bands, cin, out, g, store);
   }
   tc_cta_end<NTP>(c, id);
@@ -337,6 +376,106 @@ PAI_DEV void cta_mulmod(u4* smem, const CtaId& id, const uint32_t* a, const uint
     bool store = g < batch;
     if (!store) g = batch - 1;
     prog_mulmod<NT>(buf, mc, a + g * l, b + g * l, out + g * l, store);
+  }
+}
+
+// ---- product of many rows modulo N (homomorphic SUM of a ciphertext vector: sum(), np.mean over EncryptedNumbers,
+// phe/tests/math_test.py:44-58).  consts = [ blob ]; three buffers.  No row is ever converted to Montgomery form:
+// every mont_mul of two numbers carrying R-exponents e1, e2 (value * R^e) gives e1 + e2 - 1, a plain row has e = 0, so a
+// product tree over L rows ends at e = 1 - L however it is shaped.  The deficit is repaid by CORRECTION rows
+// K_i = R^(2^i + 1) mod N (one per set bit of L, a per-key table): as leaves of the same tree they bring the total to
+// e = 1, and one multiplication by 1 leaves the domain.  Every thread multiplies its strided share of the rows (read
+// straight from global memory), the CTA folds its threads' partials in a shared-memory tree; threads without rows
+// contribute R mod N (e = 1, neutral).  final = 0: the CTA's partial goes to row `cta` of out (input of the second
+// launch); final = 1: canonical result in row 0.  corr_bits: set bits = correction rows to append to the input.
+PAI_DEV const uint32_t* reduce_row(const uint32_t* rows, long batch, int l, const uint32_t* corr, unsigned long long corr_bits, long v) {
+  if (v < batch) return rows + v * l;
+  long j = v - batch;
+  for (int i = 0; i < 64; i++)
+    if ((corr_bits >> i) & 1ull) { if (j == 0) return corr + (long)i * l; j--; }
+  return corr;
+}
+PAI_DEV int popcount64(unsigned long long x) { int c = 0; while (x) { c += (int)(x & 1ull); x >>= 1; } return c; }
+
+template <int NT>
+PAI_DEV void cta_reduce_mul(u4* smem, const CtaId& id, const uint32_t* rows, long batch, uint32_t* out, const uint32_t* corr,
+                            unsigned long long corr_bits, int final) {
+  ModC mc;
+  modc_bind(mc, smem, NT);
+  Opnd buf[3];
+  cta_bufs<NT>(buf, 3, smem, mc_limbs(NT) / 4, id);
+  const int l = 8 * NT;
+  const long T = (long)id.ncta * id.nthr;
+  const long total = batch + popcount64(corr_bits);
+  long g = (long)id.cta * id.nthr + id.tid;
+  int cur = 0;
+  if (g < total) {
+    load_row(buf[0], reduce_row(rows, batch, l, corr, corr_bits, g), 2 * NT, 2 * NT);
+    for (g += T; g < total; g += T) {
+      Opnd r{(u4*)reduce_row(rows, batch, l, corr, corr_bits, g), 1};
+      mont_mul<NT>(buf[cur ^ 1], buf[cur], r, mc.N, mc.ninv);
+      cur ^= 1;
+    }
+  } else {
+    big_copy<NT>(buf[0], mc.R1);
+  }
+  // `cur` differs between threads (different row counts): settle every partial in buf[2]
+  big_copy<NT>(buf[2], buf[cur]);
+  int src = 2;
+#if !defined(PAI_HOSTSIM)
+  for (int step = 1; step < id.nthr; step <<= 1) {
+    const int dst = (src + 1) % 3;
+    __syncthreads();
+    if ((id.tid & (2 * step - 1)) == 0) {
+      if (id.tid + step < id.nthr) {
+        Opnd other = buf[src];
+        other.p += step;                                           // the partner's buffer in the interleaved layout
+        mont_mul<NT>(buf[dst], buf[src], other, mc.N, mc.ninv);
+      } else {
+        big_copy<NT>(buf[dst], buf[src]);                          // no partner on this level
+      }
+    }
+    src = dst;
+  }
+  const bool writer = id.tid == 0;
+  const int shift = 0;
+#else
+  // the simulation runs the threads of a CTA one after the other: the last one folds everybody's partials serially
+  const bool writer = id.tid == id.nthr - 1;
+  const int shift = id.tid;
+  if (writer) {
+    Opnd acc = buf[src], o = buf[(src + 1) % 3];
+    acc.p -= shift; o.p -= shift;                                  // thread 0's buffers
+    for (int t = 1; t < id.nthr; t++) {
+      Opnd a = buf[src];
+      a.p += t - shift;
+      mont_mul<NT>(o, acc, a, mc.N, mc.ninv);
+      big_copy<NT>(acc, o);
+    }
+  }
+#endif
+  if (writer) {
+    Opnd res = buf[src], tmp = buf[(src + 1) % 3];
+    res.p -= shift; tmp.p -= shift;
+    uint32_t* orow = out + (final ? 0 : (long)id.cta * l);
+    if (final) { mont_mul<NT>(tmp, res, mc.ONE, mc.N, mc.ninv); store_row(orow, tmp, 2 * NT); }
+    else store_row(orow, res, 2 * NT);
+  }
+}
+
+// correction rows of cta_reduce_mul: K_0 = R^2, K_(i+1) = K_i^2 / R = R^(2^(i+1) + 1)   (single thread, once per modulus)
+template <int NT>
+PAI_DEV void reduce_corr_setup(u4* smem, const CtaId& id, uint32_t* tbl, int rows) {
+  if (id.cta != 0 || id.tid != 0) return;
+  ModC mc;
+  modc_bind(mc, smem, NT);
+  Opnd buf[2];
+  cta_bufs<NT>(buf, 2, smem, mc_limbs(NT) / 4, id);
+  const int l = 8 * NT;
+  big_copy<NT>(buf[0], mc.R2);
+  for (int i = 0; i < rows; i++) {
+    store_row(tbl + (long)i * l, buf[i & 1], 2 * NT);
+    mont_sqr<NT>(buf[(i & 1) ^ 1], buf[i & 1], mc.N, mc.ninv);
   }
 }
 

@@ -74,6 +74,13 @@ struct TcPowBody {
   const uint8_t* bands; int stagger;
   PAI_MEM void run(u4* smem, const CtaId& id) const { cta_powmod_tc<NTH, W>(smem, id, base, exp, exp_limbs, out, batch, tbl, gzero, bands, stagger); }
 };
+template <int NTH, int W>
+struct TcStrausBody {
+  const uint32_t* consts; int const_quads;
+  const uint32_t* base; const uint32_t* exp; int exp_limbs; int gsz; uint32_t* out; long batch; u4* tbl; const uint32_t* gzero;
+  const uint8_t* bands; int stagger;
+  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_straus_tc<NTH, W>(smem, id, base, exp, exp_limbs, gsz, out, batch, tbl, gzero, bands, stagger); }
+};
 template <int NTP, int W>
 struct TcDecBody {
   const uint32_t* consts; int const_quads;
@@ -92,6 +99,18 @@ struct MulBody {
   const uint32_t* consts; int const_quads;
   const uint32_t* a; const uint32_t* b; uint32_t* out; long batch;
   PAI_MEM void run(u4* smem, const CtaId& id) const { cta_mulmod<NT>(smem, id, a, b, out, batch); }
+};
+template <int NT>
+struct ReduceBody {
+  const uint32_t* consts; int const_quads;
+  const uint32_t* rows; long batch; uint32_t* out; const uint32_t* corr; unsigned long long corr_bits; int final;
+  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_reduce_mul<NT>(smem, id, rows, batch, out, corr, corr_bits, final); }
+};
+template <int NT>
+struct ReduceCorrBody {
+  const uint32_t* consts; int const_quads;
+  uint32_t* tbl; int rows;
+  PAI_MEM void run(u4* smem, const CtaId& id) const { reduce_corr_setup<NT>(smem, id, tbl, rows); }
 };
 template <int NT, int W>
 struct PowBody {
@@ -380,6 +399,7 @@ struct pai_mod {
                                     // through the context's own entry points)
   // warp-per-ciphertext layout (pai_coop.cuh), built on first use: [ N | R^2 mod N | R^3 mod N ], R = 2^(32*32*coopK)
   uint32_t* d_coop = nullptr; int coopK = 0; uint32_t coop_n0inv = 0; bool coop_building = false;
+  uint32_t* d_corr = nullptr;       // correction rows R^(2^i + 1) mod N of the product reduction (cta_reduce_mul), built on first use
 };
 struct pai_pub {
   pai_mod* nsq = nullptr;           // modulus n^2; its blob is followed by n (4*NT limbs) for encrypt
@@ -519,6 +539,7 @@ void mod_free(pai_mod* m) {
   if (!m) return;
   rt_set_device(m->device);
   rt_free(m->d_blob);
+  rt_free(m->d_corr);
   if (m->d_coop) { rt_memset(m->d_coop, 0, (size_t)3 * 32 * m->coopK * 4, 0); rt_sync(0); rt_free(m->d_coop); }
   m->ws.release(); m->tmp_a.release(); m->tmp_b.release(); m->tmp_o.release(); m->tmp_s.release(); m->tmp_e.release();
   delete m;
@@ -549,6 +570,39 @@ int do_powmod(pai_mod* m, const uint32_t* base, int base_tiles, const uint32_t* 
   if (rc) return rc;
   B body{m->d_blob, cq, base, base_tiles, d_exp, exp_limbs, exp_stride, nwin_fixed, out, batch, (u4*)m->ws.get(s).tbl.p, ctr};
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
+}
+
+// product of `batch` rows modulo N -> one canonical row (two launches: per-CTA partial products, then their product
+// together with the correction rows; one launch when a single CTA covers the batch)
+const int REDUCE_CORR_ROWS = 44;
+template <int NT>
+int do_reduce_mul(pai_mod* m, const uint32_t* rows, long batch, uint32_t* out, rt_stream s) {
+  typedef ReduceBody<NT> B;
+  Geom g;
+  const int cq = mc_limbs(NT) / 4;
+  int rc = geometry<B>(m->device, NT, cq, 3, batch, g);
+  if (rc) return rc;
+  if (!m->d_corr) {                                   // per-modulus table R^(2^i + 1), built on first use
+    rc = rt_malloc((void**)&m->d_corr, (size_t)REDUCE_CORR_ROWS * m->L * 4);
+    if (rc) return rc;
+    ReduceCorrBody<NT> cb{m->d_blob, cq, m->d_corr, REDUCE_CORR_ROWS};
+    rc = rt_launch(cb, 1, g.nthr, g.smem, s);
+    if (!rc) rc = rt_sync(s);
+    if (rc) { rt_free(m->d_corr); m->d_corr = nullptr; return rc; }
+  }
+  const unsigned long long bits = (unsigned long long)batch;
+  if (g.grid == 1) {
+    B body{m->d_blob, cq, rows, batch, out, m->d_corr, bits, 1};
+    return rt_launch(body, 1, g.nthr, g.smem, s);
+  }
+  StreamWs& w = m->ws.get(s);
+  rc = w.red_a.ensure((size_t)g.grid * m->L * 4);
+  if (rc) return rc;
+  B first{m->d_blob, cq, rows, batch, (uint32_t*)w.red_a.p, m->d_corr, 0ull, 0};
+  rc = rt_launch(first, g.grid, g.nthr, g.smem, s);
+  if (rc) return rc;
+  B second{m->d_blob, cq, (const uint32_t*)w.red_a.p, (long)g.grid, out, m->d_corr, bits, 1};
+  return rt_launch(second, 1, g.nthr, g.smem, s);
 }
 
 template <int NT>
@@ -683,6 +737,29 @@ int do_powmod_tc(pai_pub* k, const uint32_t* base, const uint32_t* d_exp, int ex
   if (rc) return rc;
   B body{k->d_enc_consts, dc_pow_limbs(NTH) / 4, base, d_exp, exp_limbs, out, batch, (u4*)m->ws.get(s).tbl.p,
          m->d_blob + dc_zero_offset(NTH), k->d_tc, k->tc_stagger};
+  return rt_launch_group(body, g.grid, g.nthr, g.smem, s);
+}
+// Straus groups: one thread per group of gsz elements; gsz is chosen so that the groups fill about one wave
+template <int NTH>
+int do_straus_tc(pai_pub* k, const uint32_t* base, const uint32_t* d_exp, int exp_limbs, long batch, uint32_t* partial, long* ngroups_out,
+                 rt_stream s) {
+  typedef TcStrausBody<NTH, W_VAR> B;
+  pai_mod* m = k->nmod;
+  Geom g;
+  int rc = tc_geometry_of<B, NTH>(m->device, [](int nthr) { return tc_pow_smem_bytes<NTH>(nthr); }, 1L << 40, g);
+  if (rc) return rc;
+  const long wave = (long)g.grid * g.nthr;
+  long gsz = (batch + wave - 1) / wave;
+  if (gsz < 1) gsz = 1;
+  if (gsz > 32) gsz = 32;
+  const long ngroups = (batch + gsz - 1) / gsz;
+  rc = tc_geometry_of<B, NTH>(m->device, [](int nthr) { return tc_pow_smem_bytes<NTH>(nthr); }, ngroups, g);
+  if (rc) return rc;
+  rc = m->ws.get(s).tbl.ensure((size_t)g.grid * (((size_t)gsz << W_VAR) + 2) * 4 * NTH * g.nthr * 16);
+  if (rc) return rc;
+  B body{k->d_enc_consts, dc_pow_limbs(NTH) / 4, base, d_exp, exp_limbs, (int)gsz, partial, batch, (u4*)m->ws.get(s).tbl.p,
+         m->d_blob + dc_zero_offset(NTH), k->d_tc, k->tc_stagger};
+  *ngroups_out = ngroups;
   return rt_launch_group(body, g.grid, g.nthr, g.smem, s);
 }
 template <int NTH>
@@ -1304,6 +1381,16 @@ int pai_raw_add(pai_pub* k, const uint32_t* d_a, const uint32_t* d_b, uint32_t* 
   if (!k) { g_err = "bad argument"; return PAI_E_ARG; }
   return pai_mod_mulmod(k->nsq, d_a, d_b, d_c, batch, stream);
 }
+int pai_raw_sum(pai_pub* k, const uint32_t* d_c, long batch, uint32_t* d_out, void* stream) {
+  DeviceGuard device_guard_; (void)device_guard_;
+  if (!k || !d_c || !d_out || batch < 1) { g_err = "bad argument"; return PAI_E_ARG; }
+  pai_mod* m = k->nsq;
+  CtxLock lock_(m->mu);
+  int rc = rt_set_device(m->device);
+  if (rc) return rc;
+  DISPATCH_NT(m->NT, rc = do_reduce_mul<NT>(m, d_c, batch, d_out, (rt_stream)stream));
+  return rc;
+}
 int pai_raw_mul(pai_pub* k, const uint32_t* d_a, const uint32_t* d_s, uint32_t* d_c, int32_t* d_status, long batch, void* stream) {
   DeviceGuard device_guard_; (void)device_guard_;
   if (!k || !d_a || !d_s || !d_c || batch < 0) { g_err = "bad argument"; return PAI_E_ARG; }
@@ -1340,6 +1427,50 @@ int pai_raw_mul(pai_pub* k, const uint32_t* d_a, const uint32_t* d_s, uint32_t* 
     return rc;
   }
   return powmod_common(m, (const uint32_t*)w.w_base.p, lc, (const uint32_t*)w.w_exp.p, ln, ln, -1, d_c, batch, stream);
+}
+
+int pai_raw_dot(pai_pub* k, const uint32_t* d_a, const uint32_t* d_s, uint32_t* d_out, int32_t* d_status, long batch, void* stream) {
+  DeviceGuard device_guard_; (void)device_guard_;
+  if (!k || !d_a || !d_s || !d_out || batch < 1) { g_err = "bad argument"; return PAI_E_ARG; }
+  CtxLock lock_(k->mu);
+  pai_mod* m = k->nsq;
+  rt_stream s = (rt_stream)stream;
+  int rc = rt_set_device(m->device);
+  const int ln = k->ln, lc = 2 * k->ln;
+  StreamWs& w = k->ws.get(s);
+  if (!rc) rc = w.w_exp.ensure((size_t)batch * ln * 4);
+  if (!rc) rc = w.w_base.ensure((size_t)batch * lc * 4);
+  if (!rc) rc = w.w_flag.ensure((size_t)batch * 4 * 2);
+  if (rc) return rc;
+  int32_t* flag = (int32_t*)w.w_flag.p;
+  int32_t* status = d_status ? d_status : flag + batch;
+  {   // the reference's branch per element (phe/paillier.py:742-749): exponent s or n - s, base c or invert(c)
+    PrepBody b{nullptr, 0, k->d_nth, k->d_nth + ln, ln, d_s, (uint32_t*)w.w_exp.p, flag, batch};
+    long blocks = (batch + 127) / 128;
+    rc = rt_launch(b, (int)std::min(blocks, 65535L), 128, 0, s);
+    if (rc) return rc;
+  }
+  DISPATCH_NT(m->NT, rc = do_invert<NT>(m, d_a, lc / 8, flag, (uint32_t*)w.w_base.p, status, batch, s));
+  if (rc) return rc;
+  long nrows = batch;
+  if (k->use_tc) {                                     // Straus groups on the tensor-core path -> one row per group
+    long ngroups = 0;
+    rc = w.red_b.ensure((size_t)batch * lc * 4);       // upper bound (gsz >= 1)
+    if (rc) return rc;
+    DISPATCH_TC(k->nmod->NT, rc = do_straus_tc<NTH>(k, (const uint32_t*)w.w_base.p, (const uint32_t*)w.w_exp.p, ln, batch,
+                                                    (uint32_t*)w.red_b.p, &ngroups, s));
+    if (rc) return rc;
+    nrows = ngroups;
+  } else {                                             // plain path: every power on its own, then the product
+    rc = w.red_b.ensure((size_t)batch * lc * 4);
+    if (rc) return rc;
+    if (k->use_digit) { DISPATCH_NTH(k->nmod->NT, rc = do_powmod_digit<NTH>(k, (const uint32_t*)w.w_base.p, (const uint32_t*)w.w_exp.p, ln, (uint32_t*)w.red_b.p, batch, s)); }
+    else rc = powmod_common(m, (const uint32_t*)w.w_base.p, lc, (const uint32_t*)w.w_exp.p, ln, ln, -1, (uint32_t*)w.red_b.p, batch, stream);
+    if (rc) return rc;
+  }
+  CtxLock lock2_(m->mu);
+  DISPATCH_NT(m->NT, rc = do_reduce_mul<NT>(m, (const uint32_t*)w.red_b.p, nrows, d_out, s));
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------- private key

@@ -690,18 +690,24 @@ PAI_DEV void tc_encrypt_rows(TcCtx<NTH>& c, const uint32_t* prog, int nops, int 
 // raw_decrypt with CRT (phe/paillier.py:328-374) on the tensor-core path: the same program as prog_decrypt_digit
 // (pai_digit.cuh), every product modulo p^2 / q^2 through tc_op.  Fixed windows of W bits (secret exponent shared by
 // the batch: no digit is skipped); the 2^W-entry table lives in global memory, entry 2^W is the park slot.
+// table of powers of the base in (H[a], H[1-a]) at entries e0 .. e0 + 2^W - 1: T[0] = 1, T[1] = base, T[i] = T[i-1] * base
+template <int NTP, int W>
+PAI_DEV int tc_build_table(TcCtx<NTP>& c, int a, int e0) {
+  const DigitEnv& dc = *c.dc;
+  TC_EACH_ROW { big_copy<NTP>(tc_tbl<NTP>(c, e0, 0, rw), dc.ONEM.d0); big_copy<NTP>(tc_tbl<NTP>(c, e0, 1, rw), dc.ONEM.d1); }
+  tc_tbl_store<NTP>(c, e0 + 1, a);
+  tc_sqr_inplace<NTP>(c, a); a ^= 1;
+  tc_tbl_store<NTP>(c, e0 + 2, a);
+  for (int i = 3; i < (1 << W); i++) {
+    tc_mul_inplace<NTP>(c, a, [&](int rw) { return tc_tbl<NTP>(c, e0 + 1, 0, rw); }, [&](int rw) { return tc_tbl<NTP>(c, e0 + 1, 1, rw); });
+    a ^= 1;
+    tc_tbl_store<NTP>(c, e0 + i, a);
+  }
+  return a;
+}
 template <int NTP, int W, class FD>
 PAI_DEV int tc_pow_fixed_f(TcCtx<NTP>& c, int a, FD digit, int nwin) {          // digit(rw, window index) -> table entry of row rw
-  const DigitEnv& dc = *c.dc;
-  TC_EACH_ROW { big_copy<NTP>(tc_tbl<NTP>(c, 0, 0, rw), dc.ONEM.d0); big_copy<NTP>(tc_tbl<NTP>(c, 0, 1, rw), dc.ONEM.d1); }
-  tc_tbl_store<NTP>(c, 1, a);
-  tc_sqr_inplace<NTP>(c, a); a ^= 1;
-  tc_tbl_store<NTP>(c, 2, a);
-  for (int i = 3; i < (1 << W); i++) {
-    tc_mul_inplace<NTP>(c, a, [&](int rw) { return tc_tbl<NTP>(c, 1, 0, rw); }, [&](int rw) { return tc_tbl<NTP>(c, 1, 1, rw); });
-    a ^= 1;
-    tc_tbl_store<NTP>(c, i, a);
-  }
+  a = tc_build_table<NTP, W>(c, a, 0);
   TC_EACH_ROW {
     const int d = digit(rw, nwin - 1);
     big_copy<NTP>(tc_h<NTP>(c, a, rw), tc_tbl<NTP>(c, d, 0, rw));
@@ -720,6 +726,42 @@ PAI_DEV int tc_pow_fixed(TcCtx<NTP>& c, int a, const uint32_t* e, int nl, int nw
   return tc_pow_fixed_f<NTP, W>(c, a, [&](int, int wi) { return (int)exp_digit(e, nl, wi * W, W); }, nwin);
 }
 
+// (H[0], H[1]) <- Montgomery digit form of the plain 2*NTH-tile numbers base_row(rw) = c_0 + c_1*R:
+// (c_0, 0) * R^2 + (c_1, 0) * R^3, accumulated in table entry `tmp`.  Returns a = 0.
+template <int NTH, class FROW>
+PAI_DEV int tc_enter_wide(TcCtx<NTH>& c, FROW base_row, int tmp) {
+  const DigitEnv& dc = *c.dc;
+  for (int i = 0; i < 2; i++) {
+    const DNum E = i == 0 ? dc.RR : dc.E3;
+    tc_op<NTH, false>(
+        c, [&](int rw) { Opnd o; o.p = (u4*)(base_row(rw) + (size_t)i * 8 * NTH); o.s = 1; return o; }, [&](int) { return dc.ZERO; },
+        [&](int) { return E.d0; }, [&](int) { return E.d1; }, 0, 1);
+    if (i == 0) tc_tbl_store<NTH>(c, tmp, 1);
+    else TC_EACH_ROW {
+      DNum acc, add;
+      acc.d0 = tc_tbl<NTH>(c, tmp, 0, rw); acc.d1 = tc_tbl<NTH>(c, tmp, 1, rw);
+      add.d0 = tc_h<NTH>(c, 1, rw); add.d1 = tc_h<NTH>(c, 0, rw);
+      dadd<NTH>(acc, add, dc.N);
+    }
+  }
+  tc_tbl_load<NTH>(c, tmp, 0);
+  return 0;
+}
+// leave the domain and write the plain number Z0 + n*Z1 to out_row(rw) (a scratch table entry for padding rows)
+template <int NTH, class FOUT>
+PAI_DEV void tc_exit_plain(TcCtx<NTH>& c, int a, FOUT out_row, const bool* store) {
+  const DigitEnv& dc = *c.dc;
+  tc_mul_inplace<NTH>(c, a, [&](int) { return dc.ONE; }, [&](int) { return dc.ZERO; });
+  a ^= 1;
+  TC_EACH_ROW {
+    DNum z; z.d0 = tc_h<NTH>(c, a, rw); z.d1 = tc_h<NTH>(c, a ^ 1, rw);
+    Opnd o;
+    if (store[rw]) { o.p = (u4*)out_row(rw); o.s = 1; }
+    else o = tc_tbl<NTH>(c, 0, 0, rw);
+    digits_to_plain<NTH>(o, z, dc.N);
+  }
+}
+
 // c^k mod n^2 with per-element exponents (EncryptedNumber._raw_mul, phe/paillier.py:749-751) -- prog_powmod_digit on
 // the tensor-core path.  base rows: plain ciphertexts (2*NTH tiles = c_0 + c_1*R); nwin is uniform over the group.
 template <int NTH, int W>
@@ -727,35 +769,57 @@ PAI_DEV void tc_powmod_rows(TcCtx<NTH>& c, const uint32_t* base, const uint32_t*
                             const long* g, const bool* store) {
   const DigitEnv& dc = *c.dc;
   const int lc = 16 * NTH;
-  for (int i = 0; i < 2; i++) {                                           // (c_0, 0) * R^2 + (c_1, 0) * R^3
-    const DNum E = i == 0 ? dc.RR : dc.E3;
-    tc_op<NTH, false>(
-        c, [&](int rw) { Opnd o; o.p = (u4*)(base + g[rw] * lc + (size_t)i * 8 * NTH); o.s = 1; return o; }, [&](int) { return dc.ZERO; },
-        [&](int) { return E.d0; }, [&](int) { return E.d1; }, 0, 1);
-    if (i == 0) tc_tbl_store<NTH>(c, 0, 1);
-    else TC_EACH_ROW {
-      DNum acc, add;
-      acc.d0 = tc_tbl<NTH>(c, 0, 0, rw); acc.d1 = tc_tbl<NTH>(c, 0, 1, rw);
-      add.d0 = tc_h<NTH>(c, 1, rw); add.d1 = tc_h<NTH>(c, 0, rw);
-      dadd<NTH>(acc, add, dc.N);
-    }
-  }
-  int a = 0;
-  tc_tbl_load<NTH>(c, 0, a);
+  int a = tc_enter_wide<NTH>(c, [&](int rw) { return base + g[rw] * lc; }, 0);
   if (nwin <= 0) {
     TC_EACH_ROW { big_copy<NTH>(tc_h<NTH>(c, a, rw), dc.ONEM.d0); big_copy<NTH>(tc_h<NTH>(c, a ^ 1, rw), dc.ONEM.d1); }
   } else {
     a = tc_pow_fixed_f<NTH, W>(c, a, [&](int rw, int wi) { return (int)exp_digit(exp + g[rw] * nl, nl, wi * W, W); }, nwin);
   }
-  tc_mul_inplace<NTH>(c, a, [&](int) { return dc.ONE; }, [&](int) { return dc.ZERO; });
-  a ^= 1;
-  TC_EACH_ROW {
-    DNum z; z.d0 = tc_h<NTH>(c, a, rw); z.d1 = tc_h<NTH>(c, a ^ 1, rw);
-    Opnd o;
-    if (store[rw]) { o.p = (u4*)(out + g[rw] * lc); o.s = 1; }
-    else o = tc_tbl<NTH>(c, 0, 0, rw);
-    digits_to_plain<NTH>(o, z, dc.N);
+  tc_exit_plain<NTH>(c, a, [&](int rw) { return out + g[rw] * lc; }, store);
+}
+
+// prod_i c_i^(k_i) mod n^2 over the `gsz` elements of one row's group -- Straus' simultaneous exponentiation: one table of
+// 2^W powers per element, ONE chain of squarings shared by the whole group (the encrypted dot product of
+// examples/logistic_regression_encrypted_model.py:170-180 costs (2 + 2^W - 1 + nwin) products per element instead of
+// (2 + 2^W - 1 + nwin * (W + 1))).  Elements past the end of the batch count as exponent 0.  Table entries of element i:
+// 2^W * i ...; the two entries after the last table are the entry scratch and the park slot.
+template <int NTH, int W>
+PAI_DEV void tc_straus_rows(TcCtx<NTH>& c, const uint32_t* base, const uint32_t* exp, int nl, int gsz, int nwin, long batch,
+                            uint32_t* out, const long* g, const bool* store) {
+  const DigitEnv& dc = *c.dc;
+  const int lc = 16 * NTH;
+  const int tmp = gsz << W;
+  auto elem = [&](int rw, int i) { long j = g[rw] * gsz + i; return j < batch ? j : batch - 1; };
+  auto digit = [&](int rw, int i, int wi) {
+    long j = g[rw] * gsz + i;
+    return j < batch ? (int)exp_digit(exp + j * nl, nl, wi * W, W) : 0;
+  };
+  for (int i = 0; i < gsz; i++) {
+    int a = tc_enter_wide<NTH>(c, [&](int rw) { return base + elem(rw, i) * lc; }, tmp);
+    tc_build_table<NTH, W>(c, a, i << W);
   }
+  int a = 0;
+  if (nwin <= 0) {
+    TC_EACH_ROW { big_copy<NTH>(tc_h<NTH>(c, a, rw), dc.ONEM.d0); big_copy<NTH>(tc_h<NTH>(c, a ^ 1, rw), dc.ONEM.d1); }
+  } else {
+    for (int wi = nwin - 1; wi >= 0; wi--) {
+      if (wi < nwin - 1) for (int s = 0; s < W; s++) { tc_sqr_inplace<NTH>(c, a); a ^= 1; }
+      for (int i = 0; i < gsz; i++) {
+        if (wi == nwin - 1 && i == 0) {
+          TC_EACH_ROW {
+            const int d = digit(rw, 0, wi);
+            big_copy<NTH>(tc_h<NTH>(c, a, rw), tc_tbl<NTH>(c, d, 0, rw));
+            big_copy<NTH>(tc_h<NTH>(c, a ^ 1, rw), tc_tbl<NTH>(c, d, 1, rw));
+          }
+        } else {
+          tc_mul_inplace<NTH>(c, a, [&](int rw) { return tc_tbl<NTH>(c, (i << W) + digit(rw, i, wi), 0, rw); },
+                              [&](int rw) { return tc_tbl<NTH>(c, (i << W) + digit(rw, i, wi), 1, rw); });
+          a ^= 1;
+        }
+      }
+    }
+  }
+  tc_exit_plain<NTH>(c, a, [&](int rw) { return out + g[rw] * lc; }, store);
 }
 
 // one prime side: m_x = L(c^(x-1) mod x^2) * h mod x  -> returns the index of the half-buffer that holds it (NTP tiles)

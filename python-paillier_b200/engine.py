@@ -62,6 +62,8 @@ SYMBOLS = {
     "pai_decimal_to_limbs": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int, _vp, ctypes.c_long, ctypes.c_int, _vp]),
     "pai_raw_add": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_long, _vp]),
     "pai_raw_mul": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_long, _vp]),
+    "pai_raw_sum": (ctypes.c_int, [_vp, _vp, ctypes.c_long, _vp, _vp]),
+    "pai_raw_dot": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_long, _vp]),
     "pai_priv_create": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
     "pai_priv_destroy": (ctypes.c_int, [_vp]),
     "pai_priv_n_limbs": (ctypes.c_int, [_vp]),
@@ -351,6 +353,14 @@ class PublicContext:
 
     def raw_mul_dev(self, d_a, d_s, d_c, d_status, batch, stream=None):
         self.eng.check(self.eng.lib.pai_raw_mul(self.h, _ptr(d_a), _ptr(d_s), _ptr(d_c), _ptr(d_status), batch, _ptr(stream)))
+
+    def raw_sum_dev(self, d_c, batch, d_out, stream=None):
+        """d_out[0] = product of the rows of d_c mod n^2 (homomorphic sum of the vector), two launches."""
+        self.eng.check(self.eng.lib.pai_raw_sum(self.h, _ptr(d_c), batch, _ptr(d_out), _ptr(stream)))
+
+    def raw_dot_dev(self, d_a, d_s, d_out, d_status, batch, stream=None):
+        """d_out[0] = prod_i d_a[i]^d_s[i] mod n^2 (encrypted dot product with plaintext scalars)."""
+        self.eng.check(self.eng.lib.pai_raw_dot(self.h, _ptr(d_a), _ptr(d_s), _ptr(d_out), _ptr(d_status), batch, _ptr(stream)))
 
     # ---- host-array API (numpy uint32 limb matrices), synchronous
     def encrypt_host(self, m, r):

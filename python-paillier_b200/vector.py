@@ -431,7 +431,22 @@ class EncryptedVector(object):
         return self * (1 / scalar)
 
     def sum(self):
-        """Homomorphic sum of all elements (product tree mod n^2) -> EncryptedNumber."""
+        """Homomorphic sum of all elements -> EncryptedNumber: the product of the ciphertexts modulo n^2 in two launches
+        (pai_raw_sum: per-thread strided products, shared-memory tree per CTA, second launch over the CTA partials) --
+        the reference's sum(list) / np.mean idiom (phe/tests/math_test.py:44-58) without B - 1 sequential _raw_add calls."""
+        from .paillier import EncryptedNumber
+        if not len(self):
+            raise ValueError("empty vector")
+        ctx = self.public_key.engine_context()
+        torch = _torch()
+        v = self.decrease_exponent_to(int(self.exponents.min()))
+        out = torch.empty((1, v.limbs.shape[1]), dtype=torch.int32, device=v.limbs.device)
+        ctx.raw_sum_dev(v.limbs, len(v), out, stream=_stream(ctx))
+        return EncryptedNumber(self.public_key, limbs_to_ints(_to_host(out))[0], int(v.exponents[0]))
+
+    def sum_chain(self):
+        """The round-1 form of sum(): a chain of log2(B) pairwise raw_add launches (kept as the comparison baseline of
+        bench.py's `reductions` leg and as a cross-check in the tests)."""
         from .paillier import EncryptedNumber
         if not len(self):
             raise ValueError("empty vector")
@@ -447,10 +462,54 @@ class EncryptedVector(object):
         c = limbs_to_ints(_to_host(limbs))[0]
         return EncryptedNumber(self.public_key, c, int(v.exponents[0]))
 
+    def _encode_scalars(self, scalars):
+        if isinstance(scalars, EncryptedVector):
+            raise NotImplementedError('Good luck with that...')
+        sc = list(scalars) if not isinstance(scalars, np.ndarray) else scalars
+        if len(sc) != len(self):
+            raise ValueError("length mismatch")
+        if not isinstance(sc, np.ndarray) and any(isinstance(x, EncodedNumber) for x in sc):
+            encs = [x if isinstance(x, EncodedNumber) else EncodedNumber.encode(self.public_key, x) for x in sc]
+            return (ints_to_limbs([e.encoding for e in encs], self.public_key.engine_context().n_limbs),
+                    np.array([e.exponent for e in encs], dtype=np.int64))
+        return encode_batch(self.public_key, sc)
+
     def dot(self, scalars):
         """Homomorphic dot product sum_i self[i] * scalars[i] -> EncryptedNumber (the encrypted scoring loop of
-        examples/logistic_regression_encrypted_model.py:170-180 as two launches + a product tree)."""
-        return (self * scalars).sum()
+        examples/logistic_regression_encrypted_model.py:170-180): pai_raw_dot = Straus' simultaneous exponentiation over
+        the group of elements each thread owns (one shared chain of squarings) + the product reduction of sum().
+        Element exponents are aligned to the lowest one by folding BASE^delta into the plaintext scalar."""
+        from .paillier import EncryptedNumber
+        if not len(self):
+            raise ValueError("empty vector")
+        ctx = self.public_key.engine_context()
+        torch = _torch()
+        s_limbs, s_exps = self._encode_scalars(scalars)
+        exps = self.exponents + s_exps
+        emin = int(exps.min())
+        up = np.nonzero(exps > emin)[0]
+        if len(up):                                   # c^(k * BASE^delta) = (c^k)^(BASE^delta): alignment inside the exponent
+            n, max_int = self.public_key.n, self.public_key.max_int
+            vals = limbs_to_ints(s_limbs[up])
+            new = []
+            for k, d in zip(vals, (exps[up] - emin).tolist()):
+                f = pow(EncodedNumber.BASE, int(d))
+                mag = (n - k) if k >= n - max_int else k
+                if mag * f > max_int:
+                    raise ValueError('Integer needs to be within +/- %d but got %d' % (max_int, mag * f))
+                new.append(k * f % n)
+            s_limbs = s_limbs.copy()
+            s_limbs[up] = ints_to_limbs(new, s_limbs.shape[1])
+        out = torch.empty((1, self.limbs.shape[1]), dtype=torch.int32, device=self.limbs.device)
+        status = torch.zeros((len(self),), dtype=torch.int32, device=self.limbs.device)
+        ctx.raw_dot_dev(self.limbs, _to_dev(s_limbs, ctx), out, status, len(self), stream=_stream(ctx))
+        if bool(status.any().item()):
+            raise ZeroDivisionError('invert() no inverse exists')
+        return EncryptedNumber(self.public_key, limbs_to_ints(_to_host(out))[0], emin)
+
+    def dot_chain(self, scalars):
+        """The round-1 form of dot(): one raw_mul launch, then sum_chain()."""
+        return (self * scalars).sum_chain()
 
     # ------------------------------------------------------------------ wire format
     def to_json(self, be_secure=True):

@@ -154,3 +154,29 @@ def test_vector_inside_a_torch_stream(pkg, cuda_engine):
         w.obfuscate()
         out = sk.decrypt_batch(w)
     assert np.allclose(out, vals + 1.0, rtol=0, atol=1e-12)
+
+
+def test_fused_reductions_on_gpu(pkg, cuda_engine):
+    """EncryptedVector.sum / dot on the GPU (shared-memory product tree, second launch over the CTA partials, Straus groups
+    on the tensor-core kernels) against the launch chains of round 1 and the plaintext results."""
+    import torch
+    n, p, q = _key(1024)
+    pk = pkg.PaillierPublicKey(n)
+    sk = pkg.PaillierPrivateKey(pk, p, q)
+    rng = np.random.RandomState(3)
+    for count in (1, 5, 300, 70001):
+        vals = rng.randint(-10 ** 6, 10 ** 6, size=count).astype(np.int64)
+        v = pk.encrypt_batch(vals)
+        s_f, s_c = v.sum(), v.sum_chain()
+        assert s_f.ciphertext(False) == s_c.ciphertext(False)
+        assert sk.decrypt(s_f) == int(vals.sum())
+        ks = rng.randint(-2 ** 40, 2 ** 40, size=count).astype(np.int64)
+        d_f = v.dot(ks)
+        if count <= 300:
+            assert d_f.ciphertext(False) == v.dot_chain(ks).ciphertext(False)
+        assert sk.decrypt(d_f) == int((vals.astype(object) * ks.astype(object)).sum())
+    fl = rng.randn(2000) * 0.1
+    w = rng.randn(2000)
+    v = pk.encrypt_batch(fl)
+    assert abs(sk.decrypt(v.dot(w)) - float(fl @ w)) < 1e-6 and abs(sk.decrypt(v.sum()) - fl.sum()) < 1e-9
+    torch.cuda.synchronize()

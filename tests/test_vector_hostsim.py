@@ -137,3 +137,29 @@ def test_batched_codec_equals_scalar_codec(pkg):
         assert vec.decode_batch(pk, l2, e2) == [pkg.EncodedNumber(pk, c[0], c[1]).decode() for c in cases]
     finally:
         engine_mod._set_engine_for_tests(None)
+
+
+def test_fused_sum_and_dot_equal_the_launch_chains(pkg, env):
+    """EncryptedVector.sum / dot (pai_raw_sum / pai_raw_dot: two-launch product reduction, Straus exponentiation) give the
+    same ciphertext as the chains of raw_add / raw_mul launches they replace, and decrypt to the plaintext results --
+    mixed exponents, negative and zero scalars, lengths that are not powers of two."""
+    pk, sk, vec = env
+    rng = random.Random(12)
+    for count in (1, 2, 7, 33):
+        vals = [rng.gauss(0, 1) for _ in range(count)]
+        if count > 2:
+            vals[1] = 3                                   # an int among floats: exponent 0 next to -13
+        v = pk.encrypt_batch(vals, r_values=[rng.randrange(1, pk.n) for _ in vals])
+        s_f, s_c = v.sum(), v.sum_chain()
+        assert s_f.ciphertext(False) == s_c.ciphertext(False) and s_f.exponent == s_c.exponent
+        assert abs(sk.decrypt(s_f) - sum(vals)) < 1e-9
+        ks = [rng.gauss(0, 2) for _ in range(count)]
+        if count > 2:
+            ks[0], ks[2] = 0.0, -4
+        d_f, d_c = v.dot(ks), v.dot_chain(ks)
+        assert d_f.ciphertext(False) == d_c.ciphertext(False) and d_f.exponent == d_c.exponent
+        assert abs(sk.decrypt(d_f) - sum(a * b for a, b in zip(vals, ks))) < 1e-6
+        ki = [rng.randrange(-1000, 1000) for _ in range(count)]
+        assert sk.decrypt(v.dot(np.array(ki))) == pytest.approx(sum(a * b for a, b in zip(vals, ki)), abs=1e-6)
+    with pytest.raises(ValueError):
+        v.dot([1.0])
