@@ -143,6 +143,16 @@ int pai_limbs_to_decimal(const uint32_t* d_limbs, int limbs, uint8_t* d_text, lo
 int pai_decimal_to_limbs(const uint8_t* d_text, int width, uint32_t* d_limbs, int limbs, int32_t* d_status, long batch, int device,
                          void* stream);
 
+/* ---- batched primality testing for key generation ------------------------------------------
+ * result[i] = 1 if candidate i passes `rounds` Miller-Rabin rounds with the bases given, 0 if it is composite:
+ * util.miller_rabin (phe/util.py:381-417) for a whole batch of candidates, one thread per candidate, each with its own
+ * Montgomery constants.  The reference's getprimeover / is_prime (phe/util.py:106-124, 420-443) test one candidate at a
+ * time.  cand: [batch][limbs] (limbs a multiple of 8, candidates odd; trial division by small primes stays on the host);
+ * bases: [batch][rounds][limbs] random rows (reduced by the kernel; the caller draws them from a CSPRNG).
+ * Synchronous on return (device pointers). */
+int pai_miller_rabin(const uint32_t* d_cand, int limbs, const uint32_t* d_bases, int rounds, int32_t* d_result, long batch, int device,
+                     void* stream);
+
 /* ---- host-pointer convenience variants (H2D + kernel + D2H inside; synchronous) ---------------- */
 int pai_encrypt_host(pai_pub* k, const uint32_t* m, const uint32_t* r, uint32_t* c, long batch);
 int pai_raw_add_host(pai_pub* k, const uint32_t* a, const uint32_t* b, uint32_t* c, long batch);

@@ -9,7 +9,7 @@ from .engine import (Engine, EngineError, EngineUnavailable, ModContext, Private
 
 from .encoding import EncodedNumber  # noqa: F401,E402
 from .paillier import (DEFAULT_KEYSIZE, EncryptedNumber, PaillierPrivateKey, PaillierPrivateKeyring,  # noqa: F401,E402
-                       PaillierPublicKey, generate_paillier_keypair)
+                       PaillierPublicKey, generate_paillier_keypair, generate_paillier_keypairs)
 from . import util  # noqa: F401,E402
 from .vector import EncryptedVector  # noqa: F401,E402
 

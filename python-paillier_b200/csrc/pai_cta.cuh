@@ -533,6 +533,83 @@ PAI_DEV void cta_invert(u4* smem, const CtaId& id, const uint32_t* a, int a_tile
   }
 }
 
+// ---- invert, amortised (Montgomery's simultaneous inversion): the negative-scalar branch of _raw_mul needs invert(c, n^2)
+// for every flagged row (phe/paillier.py:745-749); a binary extended gcd per row costs as much as hundreds of modular
+// multiplications.  Here a thread owns a SEGMENT of `seg` consecutive rows: prefix products of the flagged rows in the
+// Montgomery domain (parked in the output rows), ONE extended gcd of the segment's product, then the back substitution
+// inv_i = I * P_(i-1), I <- I * a_i -- six multiplications per row.  If the product has no inverse (some row shares a factor
+// with N, or is 0) the segment falls back to one gcd per row so that every row gets its own status.  Unflagged rows are copied.
+// Four buffers (those of prog_invert).
+template <int NT>
+PAI_DEV void cta_invert_batch(u4* smem, const CtaId& id, const uint32_t* a, const int32_t* flags, uint32_t* out, int32_t* status,
+                              long batch, int seg) {
+  ModC mc;
+  modc_bind(mc, smem, NT);
+  Opnd buf[4];
+  cta_bufs<NT>(buf, 4, smem, mc_limbs(NT) / 4, id);
+  const int l = 8 * NT;
+  const long nseg = (batch + seg - 1) / seg;
+  for (long sg = (long)id.cta * id.nthr + id.tid; sg < nseg; sg += (long)id.ncta * id.nthr) {
+    const long lo = sg * seg, hi = lo + seg < batch ? lo + seg : batch;
+    // forward: P_i = P_(i-1) * a_i * R  (Montgomery form of the running product) -> out row i; unflagged rows copied
+    long last = -1, nflag = 0;
+    int cur = 0;                                             // running product in buf[cur] (0 or 1)
+    for (long i = lo; i < hi; i++) {
+      const uint32_t* row = a + i * l;
+      if (!flags[i]) {
+        const u4* src = (const u4*)row;
+        u4* dst = (u4*)(out + i * l);
+        for (int q = 0; q < 2 * NT; q++) dst[q] = src[q];
+        status[i] = 0;
+        continue;
+      }
+      load_row(buf[2], row, 2 * NT, 2 * NT);
+      if (last < 0) mont_mul<NT>(buf[cur], buf[2], mc.R2, mc.N, mc.ninv);                    // a_i * R
+      else {
+        mont_mul<NT>(buf[3], buf[2], mc.R2, mc.N, mc.ninv);
+        mont_mul<NT>(buf[cur ^ 1], buf[cur], buf[3], mc.N, mc.ninv);
+        cur ^= 1;
+      }
+      store_row(out + i * l, buf[cur], 2 * NT);
+      last = i;
+      nflag++;
+    }
+    if (last < 0) continue;
+    // one inversion of the segment's product: (A R)^-1 = A^-1 R^-1 (plain gcd), times R^3 -> A^-1 R
+    int fail = prog_invert<NT>(buf, mc, out + last * l, NT, out + last * l, false);         // result in buf[3] (x2)
+    if (fail) {
+      for (long i = lo; i < hi; i++)
+        if (flags[i]) status[i] = prog_invert<NT>(buf, mc, a + i * l, NT, out + i * l, true);
+      continue;
+    }
+    mont_mul<NT>(buf[0], buf[3], mc.R3, mc.N, mc.ninv);      // I = (a_lo .. a_last)^-1 in Montgomery form
+    int ic = 0;                                              // I lives in buf[ic] (0 or 1)
+    long prev = last;
+    for (long i = last; i >= lo; i--) {
+      if (!flags[i]) continue;
+      // find the previous flagged row (its out row holds P_prev)
+      long pj = i - 1;
+      while (pj >= lo && !flags[pj]) pj--;
+      if (pj >= lo) {
+        Opnd pp{(u4*)(out + pj * l), 1};
+        mont_mul<NT>(buf[2], buf[ic], pp, mc.N, mc.ninv);    // a_i^-1 (Montgomery form)
+      } else {
+        big_copy<NT>(buf[2], buf[ic]);                       // first flagged row: I itself
+      }
+      mont_mul<NT>(buf[3], buf[2], mc.ONE, mc.N, mc.ninv);   // leave the domain
+      if (pj >= lo) {                                        // I <- I * a_i (before row i is overwritten)
+        Opnd ai{(u4*)(a + i * l), 1};
+        mont_mul<NT>(buf[2], ai, mc.R2, mc.N, mc.ninv);
+        mont_mul<NT>(buf[ic ^ 1], buf[ic], buf[2], mc.N, mc.ninv);
+        ic ^= 1;
+      }
+      store_row(out + i * l, buf[3], 2 * NT);
+      status[i] = 0;
+      (void)prev;
+    }
+  }
+}
+
 // ---- raw_mul preparation (phe/paillier.py:742-749): s >= n - max_int  ->  flag, exponent n - s
 // Plain one-thread-per-element kernel body over global memory (a few hundred integer ops per element).
 //   n, thresh (= n - max_int): ln limbs.

@@ -127,6 +127,23 @@ struct InvBody {
   const uint32_t* a; int a_tiles; const int32_t* flags; uint32_t* out; int32_t* status; long batch;
   PAI_MEM void run(u4* smem, const CtaId& id) const { cta_invert<NT>(smem, id, a, a_tiles, flags, out, status, batch); }
 };
+template <int NT>
+struct InvBatchBody {
+  const uint32_t* consts; int const_quads;
+  const uint32_t* a; const int32_t* flags; uint32_t* out; int32_t* status; long batch; int seg;
+  PAI_MEM void run(u4* smem, const CtaId& id) const { cta_invert_batch<NT>(smem, id, a, flags, out, status, batch, seg); }
+};
+template <int NT, int W>
+struct MillerRabinBody {
+  const uint32_t* consts; int const_quads;
+  const uint32_t* cand; const uint32_t* bases; int rounds; int32_t* result; uint32_t* ws; long batch;
+  PAI_MEM void run(u4*, const CtaId& id) const {
+    const int L = 8 * NT;
+    for (long g = (long)id.cta * id.nthr + id.tid; g < batch; g += (long)id.ncta * id.nthr)
+      prog_miller_rabin<NT, W>(ws + ((long)id.cta * id.nthr + id.tid) * mr_ws_limbs<NT, W>(), cand + g * L, bases + g * (long)rounds * L, rounds,
+                               result + g);
+  }
+};
 struct RngBody {
   const uint32_t* consts; int const_quads;
   uint32_t key[8]; unsigned long long nonce; const uint32_t* n; int ln, nbits; uint32_t* out; long batch;
@@ -613,6 +630,24 @@ int do_invert(pai_mod* m, const uint32_t* a, int a_tiles, const int32_t* flags, 
   int rc = geometry<B>(m->device, NT, cq, 4, batch, g);
   if (rc) return rc;
   B body{m->d_blob, cq, a, a_tiles, flags, out, status, batch};
+  return rt_launch(body, g.grid, g.nthr, g.smem, s);
+}
+
+// flagged rows inverted with one extended gcd per segment of rows (cta_invert_batch); unflagged rows copied
+template <int NT>
+int do_invert_flagged(pai_mod* m, const uint32_t* a, const int32_t* flags, uint32_t* out, int32_t* status, long batch, rt_stream s) {
+  typedef InvBatchBody<NT> B;
+  Geom g;
+  int cq = mc_limbs(NT) / 4;
+  int rc = geometry<B>(m->device, NT, cq, 4, 1L << 40, g);                 // full grid
+  if (rc) return rc;
+  const long T = (long)g.grid * g.nthr;
+  long seg = (batch + T - 1) / T;                                          // rows per thread when the whole grid is busy
+  if (seg < 1) seg = 1;
+  if (seg > 32) seg = 32;
+  const long nseg = (batch + seg - 1) / seg;
+  g.grid = (int)std::max(1L, std::min((long)g.grid, (nseg + g.nthr - 1) / g.nthr));
+  B body{m->d_blob, cq, a, flags, out, status, batch, (int)seg};
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
 }
 
@@ -1108,6 +1143,27 @@ static int do_coop_decrypt_pow(pai_priv* k, const uint32_t* d_c, uint32_t* up, u
   return rt_launch_coop(b, grid, 32 * COOP_WARPS, smem, s);
 }
 
+// ---- batched Miller-Rabin (key generation) -------------------------------------------------------
+template <int NT>
+static int do_miller_rabin(const uint32_t* d_cand, const uint32_t* d_bases, int rounds, int32_t* d_result, long batch, int device, rt_stream s) {
+  typedef MillerRabinBody<NT, 4> B;
+#if defined(PAI_HOSTSIM)
+  const int nthr = 2;
+#else
+  const int nthr = 64;
+#endif
+  long blocks = (batch + nthr - 1) / nthr;
+  int grid = (int)std::max(1L, std::min(blocks, (long)rt_sm_count(device) * 8));
+  void* ws = nullptr;
+  int rc = rt_malloc(&ws, (size_t)grid * nthr * mr_ws_limbs<NT, 4>() * 4);
+  if (rc) return rc;
+  B body{nullptr, 0, d_cand, d_bases, rounds, d_result, (uint32_t*)ws, batch};
+  rc = rt_launch(body, grid, nthr, 0, s);
+  if (!rc) rc = rt_sync(s);
+  rt_free(ws);
+  return rc;
+}
+
 // rows per full wave of the throughput kernels (measured once per context from the launch geometry)
 static int pub_wave(pai_pub* k) {
   int rc = 0;
@@ -1340,6 +1396,17 @@ int pai_random_lt_n(pai_pub* k, const uint8_t* seed32, unsigned long long nonce,
   long blocks = (batch + 127) / 128;
   return rt_launch(b, (int)std::min(blocks, (long)rt_sm_count(k->nsq->device) * 16), 128, 0, (rt_stream)stream);
 }
+// ---- batched Miller-Rabin (key generation): do_miller_rabin above
+int pai_miller_rabin(const uint32_t* d_cand, int limbs, const uint32_t* d_bases, int rounds, int32_t* d_result, long batch, int device,
+                     void* stream) {
+  DeviceGuard device_guard_; (void)device_guard_;
+  if (!d_cand || !d_bases || !d_result || batch < 0 || rounds < 1 || limbs < 8 || limbs % 8) { g_err = "bad argument"; return PAI_E_ARG; }
+  if (batch == 0) return 0;
+  int rc = rt_set_device(device);
+  if (rc) return rc;
+  DISPATCH_NT(limbs / 8, rc = do_miller_rabin<NT>(d_cand, d_bases, rounds, d_result, batch, device, (rt_stream)stream));
+  return rc;
+}
 // ---- decimal wire format ---------------------------------------------------------------------
 static int radix_geometry(int device, int limbs, long batch, int* grid, int* nthr, size_t* smem) {
   if (limbs < 1 || limbs > 1024) { g_err = "limb count not supported"; return PAI_E_ARG; }
@@ -1415,7 +1482,7 @@ int pai_raw_mul(pai_pub* k, const uint32_t* d_a, const uint32_t* d_s, uint32_t* 
     if (rc) return rc;
   }
   // 2. base = a, or invert(a, n^2) where flagged
-  DISPATCH_NT(m->NT, rc = do_invert<NT>(m, d_a, lc / 8, flag, (uint32_t*)w.w_base.p, status, batch, s));
+  DISPATCH_NT(m->NT, rc = do_invert_flagged<NT>(m, d_a, flag, (uint32_t*)w.w_base.p, status, batch, s));
   if (rc) return rc;
   // 3. base ^ exponent mod n^2
   if (k->use_tc) {
@@ -1450,7 +1517,7 @@ int pai_raw_dot(pai_pub* k, const uint32_t* d_a, const uint32_t* d_s, uint32_t* 
     rc = rt_launch(b, (int)std::min(blocks, 65535L), 128, 0, s);
     if (rc) return rc;
   }
-  DISPATCH_NT(m->NT, rc = do_invert<NT>(m, d_a, lc / 8, flag, (uint32_t*)w.w_base.p, status, batch, s));
+  DISPATCH_NT(m->NT, rc = do_invert_flagged<NT>(m, d_a, flag, (uint32_t*)w.w_base.p, status, batch, s));
   if (rc) return rc;
   long nrows = batch;
   if (k->use_tc) {                                     // Straus groups on the tensor-core path -> one row per group

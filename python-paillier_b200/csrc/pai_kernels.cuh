@@ -484,4 +484,89 @@ PAI_DEV void mod_setup(uint32_t* blob, uint32_t* scratch) {
   mont_mul<NT>(oR3, oR2, oR2, oN, ninv);                                   // R^2 * R^2 / R = R^3
 }
 
+// ------------------------------------------------------------------------------------------------
+// Miller-Rabin on a BATCH of candidates, one thread per candidate (util.miller_rabin, phe/util.py:381-417; the
+// reference's key generation tests one candidate at a time, phe/util.py:106-124).  Every candidate is its own modulus,
+// so each thread derives its own Montgomery constants (mod_setup) in a private strip of global memory and runs the
+// generic window ladder on stride-1 operands.  `bases`: `rounds` random rows per candidate (any value < 2^(32 L); reduced
+// here; a base congruent to 0 or +-1 passes its round, as it tells nothing).  result: 1 = probably prime, 0 = composite.
+//   ws (limbs per thread): mc_limbs(NT) | 3L setup scratch | 3 buffers of L | 2^W table entries of L | d (L)
+template <int NT, int W>
+PAI_HD long mr_ws_limbs() { return mc_limbs(NT) + (long)(3 + 3 + (1 << W) + 1) * 8 * NT; }
+
+template <int NT, int W>
+PAI_DEV void prog_miller_rabin(uint32_t* ws, const uint32_t* cand, const uint32_t* bases, int rounds, int32_t* result) {
+  const int L = 8 * NT;
+  uint32_t* blob = ws;
+  uint32_t* scratch = blob + mc_limbs(NT);
+  uint32_t* b0 = scratch + 3 * L;
+  uint32_t* tblp = b0 + 3 * L;
+  uint32_t* d = tblp + (long)(1 << W) * L;
+  for (int i = 0; i < L; i++) blob[i] = cand[i];
+  // tiny / even candidates are the host's business (trial division comes first); keep the kernel total anyway
+  if (!(cand[0] & 1u)) { *result = 0; return; }
+  mod_setup<NT>(blob, scratch);
+  ModC mc;
+  modc_bind(mc, (u4*)blob, NT);
+  // n - 1 = 2^s * d
+  int s = 0;
+  {
+    for (int i = 0; i < L; i++) d[i] = cand[i];
+    d[0] &= ~1u;                                             // n - 1 (n odd)
+    int nz = 0;
+    for (int i = 0; i < L; i++) if (d[i]) nz = 1;
+    if (!nz) { *result = 0; return; }                         // n == 1
+    while (!(d[0] & 1u)) {
+      for (int i = 0; i < L - 1; i++) d[i] = (d[i] >> 1) | (d[i + 1] << 31);
+      d[L - 1] >>= 1;
+      s++;
+    }
+  }
+  const int nwin = (limbs_bitlen(d, L) + W - 1) / W;
+  PowEnv<NT> E;
+  for (int i = 0; i < 3; i++) { E.buf[i].p = (u4*)(b0 + i * L); E.buf[i].s = 1; }
+  E.tbl.p = (u4*)tblp; E.tbl.s = 1;
+  E.mc = &mc;
+  // minus one in Montgomery form: N - R1
+  int prime = 1;
+  for (int r = 0; r < rounds && prime; r++) {
+    load_row(E.buf[0], bases + (long)r * L, 2 * NT, 2 * NT);
+    mont_mul<NT>(E.buf[1], E.buf[0], mc.R2, mc.N, mc.ninv);                 // a * R mod N (any a < 2^(32 L))
+    // a = 0, 1, -1 (mod N): uninformative
+    uint32_t is0 = big_is_zero<NT>(E.buf[1]);
+    uint32_t is1 = 1, ism1 = 1;
+    {
+      uint32_t bo = 0;
+      for (int t = 0; t < NT; t++) {
+        uint32_t x[8], y[8], o[8], n[8], m1[8];
+        ld_tile(E.buf[1], t, x); ld_tile(mc.R1, t, y); ld_tile(mc.N, t, n);
+        bo = sub8b(m1, n, y, bo);                                            // N - R1, tile by tile
+        for (int i = 0; i < 8; i++) { if (x[i] != y[i]) is1 = 0; if (x[i] != m1[i]) ism1 = 0; o[i] = 0; }
+        (void)o;
+      }
+    }
+    if (is0 | is1 | ism1) continue;
+    int cur = mont_pow<NT, W, false>(E, 1, d, L, nwin);                      // a^d in Montgomery form
+    int pass = 0;
+    for (int it = 0; it < s && !pass; it++) {
+      uint32_t eq1 = 1, eqm1 = 1, bo = 0;
+      for (int t = 0; t < NT; t++) {
+        uint32_t x[8], y[8], n[8], m1[8];
+        ld_tile(E.buf[cur], t, x); ld_tile(mc.R1, t, y); ld_tile(mc.N, t, n);
+        bo = sub8b(m1, n, y, bo);
+        for (int i = 0; i < 8; i++) { if (x[i] != y[i]) eq1 = 0; if (x[i] != m1[i]) eqm1 = 0; }
+      }
+      if (eqm1 || (it == 0 && eq1)) { pass = 1; break; }
+      if (eq1) break;                                                        // a nontrivial square root of 1: composite
+      if (it + 1 < s) {
+        int nxt = cur == 2 ? 0 : cur + 1;
+        mont_sqr<NT>(E.buf[nxt], E.buf[cur], mc.N, mc.ninv);
+        cur = nxt;
+      }
+    }
+    if (!pass) prime = 0;
+  }
+  *result = prime;
+}
+
 }  // namespace pai

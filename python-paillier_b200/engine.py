@@ -62,6 +62,7 @@ SYMBOLS = {
     "pai_decimal_to_limbs": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int, _vp, ctypes.c_long, ctypes.c_int, _vp]),
     "pai_raw_add": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_long, _vp]),
     "pai_raw_mul": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_long, _vp]),
+    "pai_miller_rabin": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int, _vp, ctypes.c_long, ctypes.c_int, _vp]),
     "pai_raw_sum": (ctypes.c_int, [_vp, _vp, ctypes.c_long, _vp, _vp]),
     "pai_raw_dot": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_long, _vp]),
     "pai_priv_create": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
@@ -95,6 +96,31 @@ def decimal_to_limbs_dev(d_text, width, d_limbs, limbs, d_status, batch, device=
 
 def decimal_width(limbs, engine=None):
     return int((engine or get_engine()).lib.pai_decimal_width(limbs))
+
+
+def miller_rabin_batch(candidates, rounds=25, device=0, engine=None):
+    """[is n probably prime] for a list of odd ints > 3: `rounds` Miller-Rabin rounds per candidate on the device, random
+    bases from os.urandom (pai_miller_rabin; util.miller_rabin, phe/util.py:381-417, for a whole batch)."""
+    eng = engine or get_engine()
+    eng.require_device()
+    count = len(candidates)
+    if not count:
+        return []
+    limbs = (max(c.bit_length() for c in candidates) + 255) // 256 * 8
+    cand = ints_to_limbs(candidates, limbs)
+    bases = np.frombuffer(bytearray(os.urandom(count * rounds * limbs * 4)), dtype=np.uint32).reshape(count, rounds, limbs)
+    result = np.zeros(count, dtype=np.int32)
+    if eng.simulated:
+        eng.check(eng.lib.pai_miller_rabin(_ptr(cand), limbs, _ptr(bases), rounds, _ptr(result), count, device, None))
+        return [bool(x) for x in result]
+    import torch
+    dev = "cuda:%d" % device
+    d_c = torch.from_numpy(cand.view(np.int32).copy()).to(dev)
+    d_b = torch.from_numpy(bases.view(np.int32).copy()).to(dev)
+    d_r = torch.zeros(count, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    eng.check(eng.lib.pai_miller_rabin(_ptr(d_c), limbs, _ptr(d_b), rounds, _ptr(d_r), count, device, None))
+    return [bool(x) for x in d_r.cpu().tolist()]
 
 
 # ---------------------------------------------------------------------------- limb packing

@@ -35,6 +35,23 @@ def generate_paillier_keypair(private_keyring=None, n_length=DEFAULT_KEYSIZE):
     return public_key, private_key
 
 
+def generate_paillier_keypairs(count, n_length=DEFAULT_KEYSIZE):
+    """`count` key pairs at once (the reference's test-suite makes 100 of them one by one, phe/tests/paillier_test.py:62-71):
+    all prime candidates of a round are tested in one batched Miller-Rabin launch (util.getprimeover_batch)."""
+    from .util import getprimeover_batch
+    keys = []
+    pool = []
+    while len(keys) < count:
+        need = 2 * (count - len(keys)) + 2
+        pool += getprimeover_batch(n_length // 2, need)
+        while len(pool) >= 2 and len(keys) < count:
+            p, q = pool.pop(), pool.pop()
+            if p != q and (p * q).bit_length() == n_length:
+                pk = PaillierPublicKey(p * q)
+                keys.append((pk, PaillierPrivateKey(pk, p, q)))
+    return keys
+
+
 class PaillierPublicKey(object):
     """Public key n (g = n + 1) with the encryption methods (phe/paillier.py:71-194)."""
 

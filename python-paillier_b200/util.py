@@ -133,8 +133,39 @@ def is_prime(n, mr_rounds=25):
     return miller_rabin(n, mr_rounds)
 
 
+def is_prime_batch(candidates, mr_rounds=25):
+    """is_prime (phe/util.py:420-443) for a list of candidates: trial division by the small primes on the host, then ALL
+    survivors through one batched Miller-Rabin launch on the device (engine.miller_rabin_batch)."""
+    out = [None] * len(candidates)
+    todo = []
+    for i, n in enumerate(candidates):
+        if n <= _SMALL_PRIMES[-1]:
+            out[i] = n in _SMALL_PRIMES
+        elif any(n % p == 0 for p in _SMALL_PRIMES):
+            out[i] = False
+        else:
+            todo.append(i)
+    if todo:
+        for i, r in zip(todo, _engine.miller_rabin_batch([candidates[i] for i in todo], mr_rounds)):
+            out[i] = r
+    return out
+
+
+def getprimeover_batch(N, count=1, width=None):
+    """`count` random N-bit primes: windows of random odd candidates are sieved on the host and tested together on the
+    device until enough primes are found (the batched form of getprimeover, phe/util.py:106-124)."""
+    rnd = random.SystemRandom()
+    primes = []
+    width = width or max(64, 24 * count + N // 8)
+    while len(primes) < count:
+        cands = [rnd.randrange(1 << (N - 1), 1 << N) | 1 for _ in range(width)]
+        primes += [c for c, ok in zip(cands, is_prime_batch(cands)) if ok]
+    return primes[:count]
+
+
 def getprimeover(N):
-    """A random N-bit prime from the system's CSPRNG."""
+    """A random N-bit prime from the system's CSPRNG, one candidate at a time on the host like the reference
+    (phe/util.py:106-124); many primes at once: getprimeover_batch (device)."""
     rnd = random.SystemRandom()
     cand = rnd.randrange(1 << (N - 1), 1 << N) | 1
     while not is_prime(cand):

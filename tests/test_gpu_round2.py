@@ -180,3 +180,22 @@ def test_fused_reductions_on_gpu(pkg, cuda_engine):
     v = pk.encrypt_batch(fl)
     assert abs(sk.decrypt(v.dot(w)) - float(fl @ w)) < 1e-6 and abs(sk.decrypt(v.sum()) - fl.sum()) < 1e-9
     torch.cuda.synchronize()
+
+
+def test_batched_keygen_on_gpu(pkg, cuda_engine):
+    """generate_paillier_keypairs: prime candidates tested by the batched Miller-Rabin kernel; every prime it returns is
+    confirmed by the host-side is_prime (the reference's algorithm, phe/util.py:420-443), every key works."""
+    import importlib
+    import time
+    util = importlib.import_module("python-paillier_b200.util")
+    t0 = time.perf_counter()
+    keys = pkg.generate_paillier_keypairs(12, n_length=2048)
+    dt = time.perf_counter() - t0
+    assert len(keys) == 12 and len({pk.n for pk, _ in keys}) == 12
+    for pk, sk in keys[:4]:
+        assert pk.n.bit_length() == 2048 and util.is_prime(sk.p, 8) and util.is_prime(sk.q, 8)
+    pk, sk = keys[5]
+    assert sk.decrypt(pk.encrypt(3.5) * 2) == 7.0
+    cands = [2 ** 521 - 1, (2 ** 521 - 1) * 3 + 2, 3825123056546413051, 2 ** 1279 - 1, (2 ** 607 - 1) * (2 ** 521 - 1)]
+    assert util.is_prime_batch(cands) == [True, util.is_prime((2 ** 521 - 1) * 3 + 2), False, True, False]
+    print("12 x 2048-bit key pairs in %.1f s" % dt)
