@@ -106,7 +106,11 @@ def miller_rabin_batch(candidates, rounds=25, device=0, engine=None):
     count = len(candidates)
     if not count:
         return []
-    limbs = (max(c.bit_length() for c in candidates) + 255) // 256 * 8
+    tiles = (max(c.bit_length() for c in candidates) + 255) // 256
+    tiles = next((t for t in (1, 2, 3, 4, 6, 8, 12, 16, 24, 32) if t >= tiles), None)       # tile counts the kernels exist for
+    if tiles is None:
+        raise ValueError("candidates above 8192 bits are not supported")
+    limbs = 8 * tiles
     cand = ints_to_limbs(candidates, limbs)
     bases = np.frombuffer(bytearray(os.urandom(count * rounds * limbs * 4)), dtype=np.uint32).reshape(count, rounds, limbs)
     result = np.zeros(count, dtype=np.int32)
