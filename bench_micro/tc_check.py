@@ -9,7 +9,7 @@ _fx = importlib.import_module("python-paillier_b200.fixtures")
 
 
 def ctx(n, tc, stagger=None, pq=None):
-    os.environ["PAI_TC"] = "1" if tc else "0"
+    os.environ["PAI_TC"] = "2" if tc else "0"
     if stagger is not None:
         os.environ["PAI_TC_STAGGER"] = str(stagger)
     c = pb.PublicContext(n) if pq is None else pb.PrivateContext(*pq)

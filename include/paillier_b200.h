@@ -27,7 +27,7 @@
  *     a batch beyond whole waves of the thread-per-ciphertext kernels) of up to 0.3 wave to warp-per-ciphertext
  *     kernels with ~10x lower latency.  Environment switches, read at call time / context creation:
  *     PAI_COOP_MAX=<rows> (0 = never use the warp kernels), PAI_TC=0 (base-n digit kernels on the integer pipe instead of
- *     the tensor-core reductions), PAI_ENCRYPT_PATH=full, PAI_DECRYPT_PATH=full (full-width Montgomery kernels instead of
+ *     the tensor-core reductions; 2 = tensor-core kernels for every size they exist for, default: digit moduli >= 1024 bits), PAI_ENCRYPT_PATH=full, PAI_DECRYPT_PATH=full (full-width Montgomery kernels instead of
  *     the base-n digit kernels).  All variants return identical bits.
  */
 #ifndef PAILLIER_B200_H

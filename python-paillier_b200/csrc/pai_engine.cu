@@ -516,6 +516,14 @@ namespace {
 
 // tile counts the tensor-core kernels are instantiated for (DISPATCH_TC), up to `max_tiles`
 bool tc_supported(int tiles, int max_tiles) { return (tiles == 2 || tiles == 4 || tiles == 6 || tiles == 8 || tiles == 12) && tiles <= max_tiles; }
+// PAI_TC: "0" never, "2" whenever the kernels exist, otherwise (default) where they win: digit moduli of at least 4
+// tiles (measured: 1024-bit-key decrypt, 2 tiles per prime, is 5 % slower on the tensor-core family; 4 tiles and up win)
+bool tc_wanted(int tiles) {
+  const char* e = getenv("PAI_TC");
+  if (e && std::string(e) == "0") return false;
+  if (e && std::string(e) == "2") return true;
+  return tiles >= 4;
+}
 
 template <int NT>
 int do_setup(pai_mod* m, rt_stream s) {
@@ -1318,8 +1326,7 @@ int pai_pub_create(const uint32_t* n, int limbs, int device, pai_pub** out) {
   // the operand buffers of even one 128-thread group no longer fit shared memory)
   if (!rc && tc_supported(2 * ntp, 12)) {
     DISPATCH_TC(2 * ntp, rc = do_tc_setup<NTH>(k, 0));
-    const char* e = getenv("PAI_TC");
-    k->use_tc = !rc && k->use_digit && !(e && std::string(e) == "0");
+    k->use_tc = !rc && k->use_digit && tc_wanted(2 * ntp);
     const char* st = getenv("PAI_TC_STAGGER");
     k->tc_stagger = st && *st ? atoi(st) : 40000;
   }
@@ -1566,8 +1573,7 @@ int pai_priv_create(const uint32_t* p, const uint32_t* q, int limbs, int device,
   { const char* e = getenv("PAI_DECRYPT_PATH"); k->use_digit = !(e && std::string(e) == "full"); }
   if (!rc && tc_supported(ntp, 8)) {            // tensor-core reductions: p, q of 64 .. 256 base-256 digits (keys up to 4096 bits)
     DISPATCH_TC(ntp, rc = do_priv_tc_setup<NTH>(k, 0));
-    const char* e = getenv("PAI_TC");
-    k->use_tc = !rc && k->use_digit && !(e && std::string(e) == "0");
+    k->use_tc = !rc && k->use_digit && tc_wanted(ntp);
     const char* st = getenv("PAI_TC_STAGGER");
     k->tc_stagger = st && *st ? atoi(st) : 40000;
   }

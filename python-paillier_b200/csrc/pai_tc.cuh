@@ -220,17 +220,28 @@ PAI_DEV void tc_gemm(TcCtx<NTH>& c, int which) {
   tc_bar_sync(1 + c.grp, TC_M);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (c.row0 == 0) {
-    // one MMA covers at most 256 columns: wider moduli (D = 384 at 3072-bit keys) take two column blocks per K step
+    // Both Toeplitz operands are triangular: digit block kappa of A reaches only the columns j >= 32 kappa of A x T(N')
+    // (N'[j - k] = 0 for j < k) and only the columns j' < 32 kappa + 35 of A x T(n) (n[D - 4 + j' - k] = 0 beyond k + 3).
+    // Each K step therefore issues its MMA over that column range only (a multiple of 16), widest step first so that it
+    // initialises every column; about half of the tensor work of a full D x D product.  One MMA covers at most 256
+    // columns: wider moduli (D = 384 at 3072-bit keys) take two column blocks per K step.
     const uint32_t a0 = tc_smem_u32(c.A), b0 = tc_smem_u32(c.band[which]);
+    bool first = true;
 #pragma unroll
-    for (int kap = 0; kap < NTH; kap++) {
+    for (int step = 0; step < NTH; step++) {
+      const int kap = which == 0 ? step : NTH - 1 - step;
+      const int c_lo = which == 0 ? 32 * kap : 0;
+      const int c_hi = which == 0 ? D : (32 * kap + 48 < D ? 32 * kap + 48 : D);
       const uint64_t da = tc_desc(a0 + (uint32_t)kap * 2u * 128u, 128u, (uint32_t)(D / 16) * 128u);
 #pragma unroll
       for (int n0 = 0; n0 < D; n0 += 256) {
-        const int nn = D - n0 < 256 ? D - n0 : 256;
-        const uint64_t db = tc_desc(b0 + (uint32_t)((D - 32 - 32 * kap + n0) / 8) * 256u, 128u, 256u);
-        tc_mma(c.tmem + (uint32_t)n0, da, db, tc_idesc(nn, TC_M), kap > 0 ? 1u : 0u);
+        const int lo = c_lo > n0 ? c_lo : n0;
+        const int hi = c_hi < n0 + 256 ? c_hi : n0 + 256;
+        if (lo >= hi) continue;
+        const uint64_t db = tc_desc(b0 + (uint32_t)((D - 32 - 32 * kap + lo) / 8) * 256u, 128u, 256u);
+        tc_mma(c.tmem + (uint32_t)lo, da, db, tc_idesc(hi - lo, TC_M), first ? 0u : 1u);
       }
+      first = false;
     }
     tc_commit(c.mbar);
   }
@@ -295,9 +306,15 @@ PAI_FN void tc_prod1_mul(SOpnd A, Opnd P, XT x0, Opnd y0, TcRow* st) {
   for (int k = 0; k < 2 * NTH; k++) {
     int lo = k - NTH + 1 > 0 ? k - NTH + 1 : 0;
     int hi = k < NTH ? k : NTH - 1;
+    // y0 usually comes from the window table in L2: its next tile is requested one tile product ahead
+    uint32_t yn[8];
+    ld_tile(y0, k - lo, yn);
     for (int i = lo; i <= hi; i++) {
       uint32_t x[8], y[8];
-      ld_tile(x0, i, x); ld_tile(y0, k - i, y);
+      PAI_UNROLL
+      for (int j = 0; j < 8; j++) y[j] = yn[j];
+      if (i < hi) ld_tile(y0, k - i - 1, yn);
+      ld_tile(x0, i, x);
       tile_mac(acc, x, y);
     }
     if (k == NTH) acc.C[0] += st->nz;
@@ -314,48 +331,76 @@ PAI_FN void tc_prod1_mul(SOpnd A, Opnd P, XT x0, Opnd y0, TcRow* st) {
   }
 }
 
-// P1 (squaring): T = x0^2 with the off-diagonal tile products taken once (doubled through S)
+// r = a + small (8 limbs); returns the carry
+PAI_DEV uint32_t add8_small(uint32_t r[8], const uint32_t a[8], uint32_t small) {
+  uint32_t b[8];
+  b[0] = small;
+  PAI_UNROLL
+  for (int i = 1; i < 8; i++) b[i] = 0;
+  return add8(r, a, b);
+}
+
+// P1 (squaring): T = x0^2 = 2 * OFF + DIAG in two passes, so that the doubling is not paid per column:
+//   pass A  OFF = sum_{i<j} a_i a_j B^(i+j): plain column scanning with ONE accumulator (the round-1 form kept a second
+//           accumulator for the off-diagonal part and resolved, shifted and doubled it in every column), tiles parked
+//           where the result will go (A / park);
+//   pass B  the squares a_i^2 occupy the tile pairs (2i, 2i+1) without overlapping: T = 2*OFF + a_i^2 + carry, pair by pair.
 template <int NTH>
 PAI_FN void tc_prod1_sqr(SOpnd A, Opnd P, SOpnd x0, TcRow* st) {
-  Acc acc, S;
-  acc_clear(acc);
-  acc_clear(S);
-  uint32_t topbit = 0;
+  {
+    Acc acc;
+    acc_clear(acc);
+    for (int k = 0; k < 2 * NTH; k++) {
+      int lo = k - NTH + 1 > 0 ? k - NTH + 1 : 0;
+      int hs = k == 0 ? -1 : (k - 1) / 2;
+      for (int i = lo; i <= hs; i++) {
+        uint32_t x[8], y[8];
+        ld_tile(x0, i, x); ld_tile(x0, k - i, y);
+        tile_mac(acc, x, y);
+      }
+      uint32_t v[8];
+      acc_resolve_low(acc, v);
+      if (k < NTH) st_tile(A, k, v);
+      else st_tile(P, k - NTH, v);
+      acc_shift8(acc);
+    }
+  }
+  uint32_t carry = 0, topbit = 0;
   TcLow low; low.lowor = 0; low.top = 0;
-  for (int k = 0; k < 2 * NTH; k++) {
-    int lo = k - NTH + 1 > 0 ? k - NTH + 1 : 0;
-    int hs = k == 0 ? -1 : (k - 1) / 2;
-    for (int i = lo; i <= hs; i++) {
-      uint32_t x[8], y[8];
-      ld_tile(x0, i, x); ld_tile(x0, k - i, y);
-      tile_mac(S, x, y);
-    }
-    if ((k & 1) == 0) {
-      uint32_t x[8];
-      ld_tile(x0, k >> 1, x);
-      tile_mac(acc, x, x);
-    }
+  for (int i = 0; i < NTH; i++) {
+    uint32_t dg[2][8];
     {
-      uint32_t d[8], d2[8];
-      acc_resolve_low(S, d);
-      acc_shift8(S);
-      d2[0] = (d[0] << 1) | topbit;
+      Acc d;
+      acc_clear(d);
+      uint32_t x[8];
+      ld_tile(x0, i, x);
+      tile_mac(d, x, x);
+      acc_resolve_low(d, dg[0]);
+      acc_shift8(d);
+      acc_resolve_low(d, dg[1]);
+    }
+    PAI_UNROLL
+    for (int h = 0; h < 2; h++) {
+      const int t = 2 * i + h;
+      uint32_t o[8], o2[8], s1[8], v[8];
+      if (t < NTH) ld_tile(A, t, o);
+      else ld_tile(P, t - NTH, o);
+      o2[0] = (o[0] << 1) | topbit;
       PAI_UNROLL
-      for (int j = 1; j < 8; j++) d2[j] = (d[j] << 1) | (d[j - 1] >> 31);
-      topbit = d[7] >> 31;
-      acc_add_low(acc, d2);
+      for (int j = 1; j < 8; j++) o2[j] = (o[j] << 1) | (o[j - 1] >> 31);
+      topbit = o[7] >> 31;
+      if (t == NTH) carry += st->nz;                       // T_hi is parked with [T_lo != 0] already added
+      uint32_t c1 = add8(s1, o2, dg[h]);
+      uint32_t c2 = add8_small(v, s1, carry);
+      carry = c1 + c2;
+      if (t < NTH) {
+        st_tile(A, t, v);
+        tc_low_tile(low, v, t == NTH - 1);
+        if (t == NTH - 1) { st->nz = (low.lowor | low.top) != 0u; st->ltop = ~low.top + (low.lowor == 0u ? 1u : 0u); }
+      } else {
+        st_tile(P, t - NTH, v);
+      }
     }
-    if (k == NTH) acc.C[0] += st->nz;
-    uint32_t v[8];
-    acc_resolve_low(acc, v);
-    if (k < NTH) {
-      st_tile(A, k, v);
-      tc_low_tile(low, v, k == NTH - 1);
-      if (k == NTH - 1) { st->nz = (low.lowor | low.top) != 0u; st->ltop = ~low.top + (low.lowor == 0u ? 1u : 0u); }
-    } else {
-      st_tile(P, k - NTH, v);
-    }
-    acc_shift8(acc);
   }
 }
 
@@ -447,12 +492,18 @@ PAI_FN void tc_prod2_mul(SOpnd A, SOpnd bh, XT x0, XT x1, Opnd y0, Opnd y1, TcRo
   for (int k = 0; k < 2 * NTH; k++) {
     int lo = k - NTH + 1 > 0 ? k - NTH + 1 : 0;
     int hi = k < NTH ? k : NTH - 1;
+    uint32_t yn1[8], yn0[8];                             // table tiles requested one iteration ahead (L2 latency)
+    ld_tile(y1, k - lo, yn1);
+    ld_tile(y0, k - lo, yn0);
     for (int i = lo; i <= hi; i++) {
-      uint32_t x[8], y[8];
-      ld_tile(x0, i, x); ld_tile(y1, k - i, y);
-      tile_mac(acc, x, y);
-      ld_tile(x1, i, x); ld_tile(y0, k - i, y);
-      tile_mac(acc, x, y);
+      uint32_t x[8], ya[8], yb[8];
+      PAI_UNROLL
+      for (int j = 0; j < 8; j++) { ya[j] = yn1[j]; yb[j] = yn0[j]; }
+      if (i < hi) { ld_tile(y1, k - i - 1, yn1); ld_tile(y0, k - i - 1, yn0); }
+      ld_tile(x0, i, x);
+      tile_mac(acc, x, ya);
+      ld_tile(x1, i, x);
+      tile_mac(acc, x, yb);
     }
     uint32_t v[8];
     if (k < NTH) {
@@ -473,13 +524,24 @@ PAI_FN void tc_prod2_mul(SOpnd A, SOpnd bh, XT x0, XT x1, Opnd y0, Opnd y1, TcRo
   st->ovf2 = lo32(acc.E[0]) + acc.C[0];
 }
 
-// P2 (squaring): B = 2*x0*x1 + W (all NTH^2 cross tiles once in S, doubled on the way in)
+// P2 (squaring): B = 2*x0*x1 + W.  x1 is dead after this phase, so it is doubled IN PLACE first (x1' = 2*x1 mod R, top bit
+// tb) and the cross products run as a plain product x0 * x1' in one accumulator; tb * x0 * R enters as x0's tiles in the
+// upper columns (each read right before B_hi overwrites it).
 template <int NTH>
 PAI_FN void tc_prod2_sqr(SOpnd A, SOpnd bh, SOpnd x0, SOpnd x1, TcRow* st) {
-  Acc acc, S;
+  uint32_t tb = 0;
+  for (int t = 0; t < NTH; t++) {
+    uint32_t x[8], y[8];
+    ld_tile(x1, t, x);
+    y[0] = (x[0] << 1) | tb;
+    PAI_UNROLL
+    for (int j = 1; j < 8; j++) y[j] = (x[j] << 1) | (x[j - 1] >> 31);
+    tb = x[7] >> 31;
+    st_tile(x1, t, y);
+  }
+  Acc acc;
   acc_clear(acc);
-  acc_clear(S);
-  uint32_t topbit = 0, nz2 = 0;
+  uint32_t nz2 = 0;
   TcLow low; low.lowor = 0; low.top = 0;
   for (int k = 0; k < 2 * NTH; k++) {
     int lo = k - NTH + 1 > 0 ? k - NTH + 1 : 0;
@@ -487,17 +549,7 @@ PAI_FN void tc_prod2_sqr(SOpnd A, SOpnd bh, SOpnd x0, SOpnd x1, TcRow* st) {
     for (int i = lo; i <= hc; i++) {
       uint32_t x[8], y[8];
       ld_tile(x0, i, x); ld_tile(x1, k - i, y);
-      tile_mac(S, x, y);
-    }
-    {
-      uint32_t d[8], d2[8];
-      acc_resolve_low(S, d);
-      acc_shift8(S);
-      d2[0] = (d[0] << 1) | topbit;
-      PAI_UNROLL
-      for (int j = 1; j < 8; j++) d2[j] = (d[j] << 1) | (d[j - 1] >> 31);
-      topbit = d[7] >> 31;
-      acc_add_low(acc, d2);
+      tile_mac(acc, x, y);
     }
     uint32_t v[8];
     if (k < NTH) {
@@ -509,13 +561,18 @@ PAI_FN void tc_prod2_sqr(SOpnd A, SOpnd bh, SOpnd x0, SOpnd x1, TcRow* st) {
       tc_low_tile(low, v, k == NTH - 1);
       if (k == NTH - 1) { nz2 = (low.lowor | low.top) != 0u; st->ltop = ~low.top + (low.lowor == 0u ? 1u : 0u); }
     } else {
+      if (tb) {
+        uint32_t w[8];
+        ld_tile(x0, k - NTH, w);
+        acc_add_low(acc, w);
+      }
       if (k == NTH) acc.C[0] += st->wtop + nz2;
       acc_resolve_low(acc, v);
       st_tile(bh, k - NTH, v);
     }
     acc_shift8(acc);
   }
-  st->ovf2 = lo32(acc.E[0]) + acc.C[0] + topbit;
+  st->ovf2 = lo32(acc.E[0]) + acc.C[0];
 }
 
 // E4: z = B_hi' + hi' + [guard > ltop] (+ ovf2 * R) < 3n + 3, reduced modulo n in place (bh)

@@ -208,7 +208,7 @@ def test_all_kernel_paths_agree(pkg, cuda_engine, monkeypatch):
     k = [rng.getrandbits(64) for _ in m[:150]] + [n - 1 - rng.getrandbits(40) for _ in m[150:]]
     results = []
     paths = []
-    for env in ({"PAI_COOP_MAX": "0"}, {"PAI_TC": "0", "PAI_COOP_MAX": "0"},
+    for env in ({"PAI_TC": "2", "PAI_COOP_MAX": "0"}, {"PAI_TC": "0", "PAI_COOP_MAX": "0"},
                 {"PAI_ENCRYPT_PATH": "full", "PAI_DECRYPT_PATH": "full", "PAI_COOP_MAX": "0"}, {"PAI_COOP_MAX": "100000"}):
         for key in ("PAI_ENCRYPT_PATH", "PAI_DECRYPT_PATH", "PAI_COOP_MAX", "PAI_TC"):
             monkeypatch.delenv(key, raising=False)

@@ -20,7 +20,7 @@ def sim(pkg):
 
 def _ctx(pkg, sim, monkeypatch, n, p, q, tc):
     monkeypatch.setenv("PAI_COOP_MAX", "0")
-    monkeypatch.setenv("PAI_TC", "1" if tc else "0")
+    monkeypatch.setenv("PAI_TC", "2" if tc else "0")          # 2: the tensor-core kernels wherever they exist
     return pkg.PublicContext(n, engine=sim), pkg.PrivateContext(p, q, engine=sim)
 
 
@@ -50,10 +50,11 @@ def test_tc_family_equals_oracle_and_digit_family(pkg, sim, monkeypatch, kb, row
 
 
 def test_tc_family_key_size_coverage(pkg, sim, monkeypatch):
-    """Which keys take the tensor-core kernels: encrypt up to 3072 bits, decrypt up to 4096 bits; odd tile counts and
-    tiny primes fall back to the integer-pipe digit kernels (same bits either way, tests/test_edge_keys_hostsim.py)."""
+    """Which keys take the tensor-core kernels by default: digit moduli of 1024 bits and more (encrypt 1024 .. 3072-bit
+    keys, decrypt 2048 .. 4096-bit keys); smaller or odd-sized ones stay on the integer-pipe digit kernels (same bits either
+    way, tests/test_edge_keys_hostsim.py).  PAI_TC=2 forces the family wherever it is instantiated (used by the other test)."""
     monkeypatch.delenv("PAI_TC", raising=False)
-    for kb, enc, dec in ((256, "tc", "digit"), (512, "tc", "digit"), (1024, "tc", "tc"), (2048, "tc", "tc"), (3072, "tc", "tc"),
+    for kb, enc, dec in ((256, "digit", "digit"), (512, "digit", "digit"), (1024, "tc", "digit"), (2048, "tc", "tc"), (3072, "tc", "tc"),
                          (4096, "digit", "tc")):
         fx = load_golden("vectors_%d.json" % kb)
         pub = pkg.PublicContext(H(fx["n"]), engine=sim)
