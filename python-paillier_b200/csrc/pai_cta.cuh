@@ -191,7 +191,7 @@ PAI_DEV uint8_t* tc_cta_begin(TcCtx<NTH>& c, u4* smem, const CtaId& id, int cons
   c.tbl.s = id.nthr;
   (void)stagger_cycles;
 #else
-  __shared__ uint64_t s_mbar[2];
+  __shared__ uint64_t s_mbar[4];
   __shared__ uint32_t s_tmem;
   const int groups = id.nthr / TC_M;
   {
@@ -199,9 +199,10 @@ PAI_DEV uint8_t* tc_cta_begin(TcCtx<NTH>& c, u4* smem, const CtaId& id, int cons
     u4* dst = (u4*)bands;
     for (int i = id.tid; i < nbands * tc_band_bytes(NTH) / 16; i += id.nthr) dst[i] = src[i];
   }
-  if (id.tid == 0) { tc_mbar_init(&s_mbar[0], 1); tc_mbar_init(&s_mbar[1], 1); }
+  if (id.tid == 0) { for (int i = 0; i < 4; i++) tc_mbar_init(&s_mbar[i], 1); }
   if (id.tid < 32) {
-    if (groups == 2) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&s_tmem)), "n"(tc_tmem_cols<NTH>(2)));
+    if (groups == 4) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&s_tmem)), "n"(tc_tmem_cols<NTH>(4)));
+    else if (groups == 2) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&s_tmem)), "n"(tc_tmem_cols<NTH>(2)));
     else asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&s_tmem)), "n"(tc_tmem_cols<NTH>(1)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -220,9 +221,9 @@ PAI_DEV uint8_t* tc_cta_begin(TcCtx<NTH>& c, u4* smem, const CtaId& id, int cons
   c.prof = nullptr;
   c.tbl.p = tbl + (size_t)id.cta * tbl_cta + id.tid;
   c.tbl.s = id.nthr;
-  if (grp == 1 && stagger_cycles > 0) {                // put the groups out of phase: one multiplies while the other reduces
+  if (grp > 0 && stagger_cycles > 0) {                 // put the groups out of phase: some multiply while the others reduce
     const long long t0 = clock64();
-    while (clock64() - t0 < (long long)stagger_cycles) {}
+    while (clock64() - t0 < (long long)stagger_cycles * grp / groups * 2) {}
   }
 #endif
   return bands;
@@ -234,7 +235,8 @@ PAI_DEV void tc_cta_end(const TcCtx<NTH>& c, const CtaId& id) {
   __syncthreads();
   if (id.tid < 32) {
     const uint32_t t0 = c.tmem - (uint32_t)(c.grp * 32 * NTH);
-    if (id.nthr / TC_M == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(t0), "n"(tc_tmem_cols<NTH>(2)));
+    if (id.nthr / TC_M == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(t0), "n"(tc_tmem_cols<NTH>(4)));
+    else if (id.nthr / TC_M == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(t0), "n"(tc_tmem_cols<NTH>(2)));
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(t0), "n"(tc_tmem_cols<NTH>(1)));
   }
 #else

@@ -242,6 +242,23 @@ struct LBody {
   }
 };
 
+}  // namespace
+#if !defined(PAI_HOSTSIM)
+// tensor-core kernels of digit moduli with at most 4 tiles (128 base-256 digits: 2048-bit-key decrypt, 1024-bit-key encrypt)
+// keep 3 x 128 bytes per thread in shared memory, so FOUR 128-thread groups fit an SM (4 x 128 TMEM columns = all 512):
+// 16 warps instead of 8 to keep the integer pipe busy while other groups wait for their GEMMs -- at 128 registers a thread
+namespace pai {
+template <int W> struct BodyMaxThreads<TcDecBody<2, W>> { static const int v = 512; };
+template <int W> struct BodyMaxThreads<TcDecBody<4, W>> { static const int v = 512; };
+template <> struct BodyMaxThreads<TcEncBody<2>> { static const int v = 512; };
+template <> struct BodyMaxThreads<TcEncBody<4>> { static const int v = 512; };
+template <int W> struct BodyMaxThreads<TcPowBody<2, W>> { static const int v = 512; };
+template <int W> struct BodyMaxThreads<TcPowBody<4, W>> { static const int v = 512; };
+template <int W> struct BodyMaxThreads<TcStrausBody<2, W>> { static const int v = 512; };
+template <int W> struct BodyMaxThreads<TcStrausBody<4, W>> { static const int v = 512; };
+}  // namespace pai
+#endif
+namespace {
 const int W_ENC = 6, W_DEC = 5, W_VAR = 4;   // W_ENC: sliding window (32 odd powers); W_DEC/W_VAR: fixed windows
 #if defined(PAI_HOSTSIM)
 const int NTHR_MAX = 2;      // the CPU simulation runs lanes one after the other: keep CTAs tiny
@@ -516,13 +533,14 @@ namespace {
 
 // tile counts the tensor-core kernels are instantiated for (DISPATCH_TC), up to `max_tiles`
 bool tc_supported(int tiles, int max_tiles) { return (tiles == 2 || tiles == 4 || tiles == 6 || tiles == 8 || tiles == 12) && tiles <= max_tiles; }
-// PAI_TC: "0" never, "2" whenever the kernels exist, otherwise (default) where they win: digit moduli of at least 4
-// tiles (measured: 1024-bit-key decrypt, 2 tiles per prime, is 5 % slower on the tensor-core family; 4 tiles and up win)
-bool tc_wanted(int tiles) {
+// PAI_TC: "0" never, "2" whenever the kernels exist, otherwise (default) where they were measured to win: encrypt for digit
+// moduli n of at least 4 tiles (1024-bit keys and up), decrypt for primes of at least 2 tiles (1024-bit keys and up; with
+// four 128-thread groups per SM: 3.73 M/s against 3.17 M/s on the integer pipe at 1024-bit keys)
+bool tc_wanted(int tiles, int min_tiles) {
   const char* e = getenv("PAI_TC");
   if (e && std::string(e) == "0") return false;
   if (e && std::string(e) == "2") return true;
-  return tiles >= 4;
+  return tiles >= min_tiles;
 }
 
 template <int NT>
@@ -717,7 +735,8 @@ int tc_geometry_of(int device, SmemFn smem_bytes, long batch, Geom& g) {
   return 0;
 #else
   const size_t max_smem = rt_max_smem(device);
-  for (int nthr = 2 * TC_M; nthr >= TC_M; nthr -= TC_M) {
+  for (int nthr = 4 * TC_M; nthr >= TC_M; nthr /= 2) {                      // 4, 2 or 1 groups of 128 threads
+    if (nthr > BodyMaxThreads<B>::v) continue;
     size_t smem = smem_bytes(nthr);
     if (smem + 64 > max_smem || (nthr / TC_M) * 32 * NTH > 512) continue;      // shared memory, TMEM columns
     int occ = rt_occupancy<B>(nthr, smem);
@@ -1326,7 +1345,7 @@ int pai_pub_create(const uint32_t* n, int limbs, int device, pai_pub** out) {
   // the operand buffers of even one 128-thread group no longer fit shared memory)
   if (!rc && tc_supported(2 * ntp, 12)) {
     DISPATCH_TC(2 * ntp, rc = do_tc_setup<NTH>(k, 0));
-    k->use_tc = !rc && k->use_digit && tc_wanted(2 * ntp);
+    k->use_tc = !rc && k->use_digit && tc_wanted(2 * ntp, 4);
     const char* st = getenv("PAI_TC_STAGGER");
     k->tc_stagger = st && *st ? atoi(st) : 40000;
   }
@@ -1573,7 +1592,7 @@ int pai_priv_create(const uint32_t* p, const uint32_t* q, int limbs, int device,
   { const char* e = getenv("PAI_DECRYPT_PATH"); k->use_digit = !(e && std::string(e) == "full"); }
   if (!rc && tc_supported(ntp, 8)) {            // tensor-core reductions: p, q of 64 .. 256 base-256 digits (keys up to 4096 bits)
     DISPATCH_TC(ntp, rc = do_priv_tc_setup<NTH>(k, 0));
-    k->use_tc = !rc && k->use_digit && tc_wanted(ntp);
+    k->use_tc = !rc && k->use_digit && tc_wanted(ntp, 2);
     const char* st = getenv("PAI_TC_STAGGER");
     k->tc_stagger = st && *st ? atoi(st) : 40000;
   }

@@ -62,8 +62,13 @@ static inline int rt_sync(rt_stream s) { RT_CHECK(cudaStreamSynchronize(s)); ret
 static inline int rt_sm_count(int dev) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n > 0 ? n : 1; }
 static inline size_t rt_max_smem(int dev) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); return (size_t)n; }
 
+// threads per CTA a body may be launched with (sets the register budget: 256 -> 255 registers, 512 -> 128); bodies that
+// want wider CTAs specialise this (pai_engine.cu: the tensor-core kernels of small digit moduli run 4 groups of 128)
 template <class Body>
-__global__ void __launch_bounds__(256) k_body(Body b) {
+struct BodyMaxThreads { static const int v = 256; };
+
+template <class Body>
+__global__ void __launch_bounds__(BodyMaxThreads<Body>::v) k_body(Body b) {
   extern __shared__ u4 smem[];
   CtaId id{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
   cta_load_consts(smem, id, b.consts, b.const_quads);

@@ -50,11 +50,11 @@ def test_tc_family_equals_oracle_and_digit_family(pkg, sim, monkeypatch, kb, row
 
 
 def test_tc_family_key_size_coverage(pkg, sim, monkeypatch):
-    """Which keys take the tensor-core kernels by default: digit moduli of 1024 bits and more (encrypt 1024 .. 3072-bit
-    keys, decrypt 2048 .. 4096-bit keys); smaller or odd-sized ones stay on the integer-pipe digit kernels (same bits either
-    way, tests/test_edge_keys_hostsim.py).  PAI_TC=2 forces the family wherever it is instantiated (used by the other test)."""
+    """Which keys take the tensor-core kernels by default: encrypt for 1024 .. 3072-bit keys, decrypt for 1024 .. 4096-bit
+    keys; smaller or odd-sized ones stay on the integer-pipe digit kernels (same bits either way,
+    tests/test_edge_keys_hostsim.py).  PAI_TC=2 forces the family wherever it is instantiated (used by the other test)."""
     monkeypatch.delenv("PAI_TC", raising=False)
-    for kb, enc, dec in ((256, "digit", "digit"), (512, "digit", "digit"), (1024, "tc", "digit"), (2048, "tc", "tc"), (3072, "tc", "tc"),
+    for kb, enc, dec in ((256, "digit", "digit"), (512, "digit", "digit"), (1024, "tc", "tc"), (2048, "tc", "tc"), (3072, "tc", "tc"),
                          (4096, "digit", "tc")):
         fx = load_golden("vectors_%d.json" % kb)
         pub = pkg.PublicContext(H(fx["n"]), engine=sim)
