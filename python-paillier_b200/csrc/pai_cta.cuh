@@ -285,7 +285,7 @@ PAI_DEV void cta_powmod_tc(u4* smem, const CtaId& id, const uint32_t* base, cons
   c.dc = &dc;
   tc_cta_begin<NTH>(c, smem, id, dc_pow_limbs(NTH), 2, gbands, tbl, (1 << W) + 1, stagger_cycles);
 #if !defined(PAI_HOSTSIM)
-  __shared__ int s_nwin[2];
+  __shared__ int s_nwin[4];
 #endif
   for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
     long g[TC_RL]; bool store[TC_RL];
@@ -317,7 +317,7 @@ PAI_DEV void cta_straus_tc(u4* smem, const CtaId& id, const uint32_t* base, cons
   tc_cta_begin<NTH>(c, smem, id, dc_pow_limbs(NTH), 2, gbands, tbl, (gsz << W) + 2, stagger_cycles);
   const long ngroups = (batch + gsz - 1) / gsz;
 #if !defined(PAI_HOSTSIM)
-  __shared__ int s_nwin[2];
+  __shared__ int s_nwin[4];
 #endif
   for (long chunk = id.cta; chunk * id.nthr < ngroups; chunk += id.ncta) {
     long g[TC_RL]; bool store[TC_RL];
