@@ -65,7 +65,7 @@ def sliding_counts(e, w):
     return nsq, nmul
 
 
-def executed_macs(kb, n=None, scalar_bits=64, enc_path="digit", dec_path="digit"):
+def executed_macs(kb, n=None, scalar_bits=64, enc_path="digit", dec_path="digit", mul_path=None):
     """32x32->64 MACs the kernels really issue on the INTEGER pipe per op, counted from the loops.
     digit family (pai_digit.cuh): dsqr<T> = T(T+1)/2 + 3 T^2 tile products, dmul<T> = 5 T^2, a tile product = 64 MACs,
     plus 2T truncated quotient products (mul_lo8, 36 MACs) per dsqr/dmul (2048-bit: 228 + 16 and 320 + 16).
@@ -96,7 +96,7 @@ def executed_macs(kb, n=None, scalar_bits=64, enc_path="digit", dec_path="digit"
     dec_tensor = 2 * (s_sq + s_mul) * tens_d
     add = 2 * mont(2 * th)
     nw = -(-scalar_bits // 4)
-    dsqr_i, dmul_i, _ = ops(th, "digit")
+    dsqr_i, dmul_i, _ = ops(th, mul_path or enc_path)          # raw_mul runs on the same kernel family as encrypt
     mul = 2 * dmul_i + dsqr_i + 13 * dmul_i + (nw - 1) * (4 * dsqr_i + dmul_i) + dmul_i + 64 * th * th
     return {"encrypt": enc, "decrypt": dec, "add": add, "mul": mul, "mont_full": mont(2 * th),
             "encrypt_tensor_u8_macs": enc_tensor, "decrypt_tensor_u8_macs": dec_tensor}
@@ -624,7 +624,7 @@ def leg_add_mul(dev, args, pb, np, key, pool, state, peak_mac_s):
         assert to_ints(pb, np, kept["u64"][1][ti]) == pool.oracle("mul", key, list(zip(a, ks))), "raw_mul differs from the oracle"
         out["parity"] = {"rows_checked_vs_gmp_oracle": len(idx), "add": "bit-exact", "mul": "bit-exact (u64: %d rows; float / negative mixes: 64 rows each)" % len(idx)}
     W = dev.world
-    ex, ca = executed_macs(KEY_BITS, n), canonical_macs(KEY_BITS)
+    ex, ca = executed_macs(KEY_BITS, n, enc_path=pub.kernel_path()), canonical_macs(KEY_BITS)
     add_s, mul_s = W * B / (add_ms * 1e-3), W * B / (mul_u64 * 1e-3)
     hbm = _hbm_peak()
     out.update({
@@ -632,12 +632,12 @@ def leg_add_mul(dev, args, pb, np, key, pool, state, peak_mac_s):
                     "roofline": {"bound": "int_pipe", "frac": add_s / W * ex["add"] / peak_mac_s, "canonical_frac": add_s / W * ca["add"] / peak_mac_s,
                                  "executed_macs_per_op": ex["add"], "hbm_gbs": add_s / W * 1536 / 1e9, "hbm_frac": add_s / W * 1536 / 1e9 / hbm[0]}},
         "raw_mul_u64": {"value": mul_s, "unit": "muls/s", "ms": mul_u64,
-                        "kernel": "rawmul_prep + k_body<InvBody<16>> (copy rows) + k_body<PowDigitBody<8,4>>",
+                        "kernel": "rawmul_prep + k_body<InvBatchBody<16>> (copy rows) + " + ("k_body<TcPowBody<8,4>>" if pub.kernel_path() == "tc" else "k_body<PowDigitBody<8,4>>"),
                         "roofline": {"bound": "int_pipe", "frac": mul_s / W * ex["mul"] / peak_mac_s,
                                      "canonical_frac": mul_s / W * ca["mul"] / peak_mac_s, "executed_macs_per_op": ex["mul"]}},
         "raw_mul_float_encoded": {"value": W * B / (mul_f * 1e-3), "unit": "muls/s", "ms": mul_f,
                                   "note": "EncodedNumber.encode(N(0, 0.1) float64): 53-56-bit exponents, half of them negative -> invert + powmod"},
-        "raw_mul_negative": {"value": W * B / (mul_n * 1e-3), "unit": "muls/s", "ms": mul_n, "note": "k = n - u64: every row takes invert(c, n^2) first"},
+        "raw_mul_negative": {"value": W * B / (mul_n * 1e-3), "unit": "muls/s", "ms": mul_n, "note": "k = n - u64: every row takes invert(c, n^2) first (amortised: one extended gcd per segment of rows, cta_invert_batch)"},
     })
     return out
 
@@ -814,7 +814,11 @@ def leg_federated(dev, args, pb, np, key, cores):
     sk = pb.PaillierPrivateKey(pk, p, q)
     D, C = args.fed_dim, 5
     grads = [np.random.RandomState(43 + i).randn(D) * 0.1 for i in range(C)]
-    pk.encrypt_batch(grads[0][:256])
+    # warm-up: one small round through every call of the protocol (context creation, workspace allocation of this key's
+    # contexts -- a fresh key pair, as a client would have -- are not part of a round)
+    w = [pk.encrypt_batch(g[:D // 2 + 7]) for g in grads[:2]]
+    sk.decrypt_batch(w[0] + w[1])
+    del w
     torch.cuda.synchronize()
     t = {}
     t0 = time.perf_counter()
