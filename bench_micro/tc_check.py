@@ -25,7 +25,9 @@ def run(kb, waves, staggers):
     for stg in staggers:
         pub = ctx(n, True, stg)
         wave = pub.wave()
-        B = int(waves * wave) + 77
+        dwave = ctx(n, True, stg, (p, q)).wave()
+        B = max(int(waves * wave), dwave) + 77                 # encrypt: `waves` full waves + a 77-row tail
+        Bd = (B - 77) // dwave * dwave + 77                     # decrypt: whole waves of ITS kernel + the same tail
         if first:
             d_m = torch.empty((B, pub.n_limbs), dtype=torch.int32, device="cuda")
             d_r = torch.empty_like(d_m)
@@ -66,8 +68,8 @@ def run(kb, waves, staggers):
                                    "roundtrip": bool((d_dref == d_m).all().item())}
         d_d = torch.zeros((B, pub.n_limbs), dtype=torch.int32, device="cuda")
         priv.decrypt_dev(d_ref, d_d, B); torch.cuda.synchronize()
-        e0.record(); priv.decrypt_dev(d_ref, d_d, B); e1.record(); torch.cuda.synchronize()
-        res["tc_decrypt_stagger_%d" % stg] = {"ms": e0.elapsed_time(e1), "per_s": B / e0.elapsed_time(e1) * 1e3, "wave": priv.wave(),
+        e0.record(); priv.decrypt_dev(d_ref, d_d, Bd); e1.record(); torch.cuda.synchronize()
+        res["tc_decrypt_stagger_%d" % stg] = {"rows": Bd, "ms": e0.elapsed_time(e1), "per_s": Bd / e0.elapsed_time(e1) * 1e3, "wave": priv.wave(),
                                                "roundtrip": bool((d_d == d_m).all().item()), "rows_differing": int((d_d != d_m).any(dim=1).sum().item())}
         first = False
         print(json.dumps(res), flush=True)

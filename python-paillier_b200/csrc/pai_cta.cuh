@@ -136,12 +136,12 @@ PAI_DEV void cta_encrypt_digit(u4* smem, const CtaId& id, const uint32_t* prog, 
 }
 
 // ---- kernels with the reductions on the tensor cores (pai_tc.cuh).  Shared memory map of all of them:
-//   [ constants | pad | bands (2 per digit modulus) | H0 | H1 | A (one per 128-thread group) ]
-// H0/H1: the two half-buffers of every thread (interleaved, stride nthr); A: the groups' MMA operand buffers.
+//   [ constants | pad | bands (2 per digit modulus) | X | H1 (unless tc_x1_global) | A (one per 128-thread group) ]
+// X/H1: the half-buffers of the digits x0 / x1 of every thread (interleaved, stride nthr); A: the groups' MMA operand buffers.
 template <int NTH>
 PAI_HD size_t tc_smem_bytes(int const_limbs, int nbands, int nthr) {
   const int groups = nthr >= TC_M ? nthr / TC_M : 1;
-  return (size_t)const_limbs * 4 + 256 + (size_t)nbands * tc_band_bytes(NTH) + 2 * (size_t)(2 * NTH) * nthr * 16 +
+  return (size_t)const_limbs * 4 + 256 + (size_t)nbands * tc_band_bytes(NTH) + (tc_x1_global<NTH>() ? 1 : 2) * (size_t)(2 * NTH) * nthr * 16 +
          (size_t)groups * TC_M * 32 * NTH;
 }
 template <int NTH>
@@ -150,18 +150,28 @@ template <int NTH>
 PAI_HD size_t tc_pow_smem_bytes(int nthr) { return tc_smem_bytes<NTH>(dc_pow_limbs(NTH), 2, nthr); }
 template <int NTP>
 PAI_HD size_t tc_dec_smem_bytes(int nthr) { return tc_smem_bytes<NTP>((2 * (dside_limbs<NTP>() / 4) + 2 * NTP) * 4, 4, nthr); }
+// accumulator slots of D = 32*NTH columns in the 512 TMEM columns of an SM
+PAI_HD int tc_tmem_slots(int NTH) { int n = 512 / (32 * NTH); return n < 1 ? 1 : (n > 4 ? 4 : n); }
+// columns to allocate for `groups` groups: all 512 when the groups share slots, else the next power of two
 template <int NTH>
 #if !defined(PAI_HOSTSIM)
 __host__ __device__
 #endif
-constexpr int tc_tmem_cols(int groups) { int need = groups * 32 * NTH, c = 32; while (c < need && c < 512) c *= 2; return c; }
+constexpr int tc_tmem_cols(int groups) {
+  int slots = 512 / (32 * NTH);
+  if (groups > slots) return 512;
+  int need = groups * 32 * NTH, c = 32;
+  while (c < need && c < 512) c *= 2;
+  return c;
+}
 
 // Set-up shared by the tensor-core kernels: copies the bands to shared memory, allocates TMEM and the groups' mbarriers,
-// fills in the context of the calling thread.  Returns the shared-memory address of the bands.  `entries`: table entries
-// per thread including the park slot.
+// fills in the context of the calling thread.  Returns the shared-memory address of the bands.  `entries`: user table
+// entries per thread; two more follow: the park slot and (tc_x1_global) the home of the high digit x1.
 template <int NTH>
 PAI_DEV uint8_t* tc_cta_begin(TcCtx<NTH>& c, u4* smem, const CtaId& id, int const_limbs, int nbands, const uint8_t* gbands, u4* tbl,
                               int entries, int stagger_cycles) {
+  constexpr bool x1_global = tc_x1_global<NTH>();
   const int D = 32 * NTH;
   uint8_t* base = (uint8_t*)smem;
   size_t off = (size_t)const_limbs * 4;
@@ -171,14 +181,14 @@ PAI_DEV uint8_t* tc_cta_begin(TcCtx<NTH>& c, u4* smem, const CtaId& id, int cons
   off = (off + 127) & ~(size_t)127;
 #endif
   uint8_t* bands = base + off;
-  u4* H0 = (u4*)(bands + (size_t)nbands * tc_band_bytes(NTH));
-  u4* H1 = H0 + (size_t)(2 * NTH) * id.nthr;
-  uint8_t* A0 = (uint8_t*)(H1 + (size_t)(2 * NTH) * id.nthr);
-  c.H[0] = H0; c.H[1] = H1;
+  u4* X = (u4*)(bands + (size_t)nbands * tc_band_bytes(NTH));
+  u4* H1s = X + (size_t)(2 * NTH) * id.nthr;
+  uint8_t* A0 = (uint8_t*)(x1_global ? H1s : H1s + (size_t)(2 * NTH) * id.nthr);
+  c.X = X;
   c.band[0] = bands; c.band[1] = bands + tc_band_bytes(NTH);
-  c.slots = entries - 1;
+  c.slots = entries;                                         // park slot = entry `entries`, x1 home = entry `entries` + 1
   c.nthr = id.nthr;
-  const size_t tbl_cta = (size_t)entries * 4 * NTH * id.nthr;
+  const size_t tbl_cta = (size_t)(entries + 2) * 4 * NTH * id.nthr;
   (void)D;
 #if defined(PAI_HOSTSIM)
   // one call walks the TC_RL rows of the CTA (id.nthr == TC_RL); they sit in different 8-row groups of the operand
@@ -193,15 +203,17 @@ PAI_DEV uint8_t* tc_cta_begin(TcCtx<NTH>& c, u4* smem, const CtaId& id, int cons
 #else
   __shared__ uint64_t s_mbar[4];
   __shared__ uint32_t s_tmem;
+  __shared__ uint32_t s_locks[8];
   const int groups = id.nthr / TC_M;
   {
     const u4* src = (const u4*)gbands;
     u4* dst = (u4*)bands;
     for (int i = id.tid; i < nbands * tc_band_bytes(NTH) / 16; i += id.nthr) dst[i] = src[i];
   }
-  if (id.tid == 0) { for (int i = 0; i < 4; i++) tc_mbar_init(&s_mbar[i], 1); }
+  if (id.tid == 0) { for (int i = 0; i < 4; i++) tc_mbar_init(&s_mbar[i], 1); for (int i = 0; i < 8; i++) s_locks[i] = 0; }
   if (id.tid < 32) {
     if (groups == 4) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&s_tmem)), "n"(tc_tmem_cols<NTH>(4)));
+    else if (groups == 3) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&s_tmem)), "n"(tc_tmem_cols<NTH>(3)));
     else if (groups == 2) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&s_tmem)), "n"(tc_tmem_cols<NTH>(2)));
     else asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&s_tmem)), "n"(tc_tmem_cols<NTH>(1)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -212,10 +224,15 @@ PAI_DEV uint8_t* tc_cta_begin(TcCtx<NTH>& c, u4* smem, const CtaId& id, int cons
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int grp = id.tid / TC_M;
   c.grp = grp;
+  c.ngroups = groups;
+  c.nslots = tc_tmem_slots(NTH);
+  c.locks = s_locks;
+  c.slot = grp;
   c.A = (u4*)(A0 + (size_t)grp * TC_M * D);
   c.tid = id.tid;
   c.row0 = id.tid % TC_M;
-  c.tmem = s_tmem + (uint32_t)(grp * D);
+  c.tmem_base = s_tmem;
+  c.tmem = s_tmem + (uint32_t)((groups > c.nslots ? 0 : grp) * D);
   c.mbar = &s_mbar[grp];
   c.phase = 0;
   c.prof = nullptr;
@@ -226,6 +243,8 @@ PAI_DEV uint8_t* tc_cta_begin(TcCtx<NTH>& c, u4* smem, const CtaId& id, int cons
     while (clock64() - t0 < (long long)stagger_cycles * grp / groups * 2) {}
   }
 #endif
+  if (x1_global) c.H1 = tc_tbl<NTH>(c, entries + 1, 0, 0);
+  else { c.H1.p = H1s + c.tid; c.H1.s = id.nthr; }
   return bands;
 }
 template <int NTH>
@@ -234,9 +253,11 @@ PAI_DEV void tc_cta_end(const TcCtx<NTH>& c, const CtaId& id) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (id.tid < 32) {
-    const uint32_t t0 = c.tmem - (uint32_t)(c.grp * 32 * NTH);
-    if (id.nthr / TC_M == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(t0), "n"(tc_tmem_cols<NTH>(4)));
-    else if (id.nthr / TC_M == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(t0), "n"(tc_tmem_cols<NTH>(2)));
+    const uint32_t t0 = c.tmem_base;
+    const int groups = id.nthr / TC_M;
+    if (groups == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(t0), "n"(tc_tmem_cols<NTH>(4)));
+    else if (groups == 3) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(t0), "n"(tc_tmem_cols<NTH>(3)));
+    else if (groups == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(t0), "n"(tc_tmem_cols<NTH>(2)));
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(t0), "n"(tc_tmem_cols<NTH>(1)));
   }
 #else
@@ -260,7 +281,7 @@ PAI_DEV void cta_encrypt_tc(u4* smem, const CtaId& id, const uint32_t* prog, int
   digit_bind_enc<NTH>(dc, smem, gzero);
   TcCtx<NTH> c;
   c.dc = &dc;
-  tc_cta_begin<NTH>(c, smem, id, dc_enc_limbs(NTH), 2, gbands, tbl, nodd + 2, stagger_cycles);
+  tc_cta_begin<NTH>(c, smem, id, dc_enc_limbs(NTH), 2, gbands, tbl, nodd + 1, stagger_cycles);
 #if !defined(PAI_HOSTSIM)
   c.prof = prof ? prof + ((size_t)id.cta * (id.nthr / 32) + id.tid / 32) * 16 : nullptr;
 #else
@@ -283,7 +304,7 @@ PAI_DEV void cta_powmod_tc(u4* smem, const CtaId& id, const uint32_t* base, cons
   digit_bind_pow<NTH>(dc, smem, gzero);
   TcCtx<NTH> c;
   c.dc = &dc;
-  tc_cta_begin<NTH>(c, smem, id, dc_pow_limbs(NTH), 2, gbands, tbl, (1 << W) + 1, stagger_cycles);
+  tc_cta_begin<NTH>(c, smem, id, dc_pow_limbs(NTH), 2, gbands, tbl, (1 << W), stagger_cycles);
 #if !defined(PAI_HOSTSIM)
   __shared__ int s_nwin[4];
 #endif
@@ -314,7 +335,7 @@ PAI_DEV void cta_straus_tc(u4* smem, const CtaId& id, const uint32_t* base, cons
   digit_bind_pow<NTH>(dc, smem, gzero);
   TcCtx<NTH> c;
   c.dc = &dc;
-  tc_cta_begin<NTH>(c, smem, id, dc_pow_limbs(NTH), 2, gbands, tbl, (gsz << W) + 2, stagger_cycles);
+  tc_cta_begin<NTH>(c, smem, id, dc_pow_limbs(NTH), 2, gbands, tbl, (gsz << W) + 1, stagger_cycles);
   const long ngroups = (batch + gsz - 1) / gsz;
 #if !defined(PAI_HOSTSIM)
   __shared__ int s_nwin[4];
@@ -356,7 +377,7 @@ PAI_DEV void cta_decrypt_tc(u4* smem, const CtaId& id, int nwin_p, int nwin_q, c
   Opnd pinvqM{smem + 2 * (dside_limbs<NTP>() / 4), 1};
   TcCtx<NTP> c;
   c.dc = &P.dc;
-  uint8_t* bands = tc_cta_begin<NTP>(c, smem, id, (2 * (dside_limbs<NTP>() / 4) + 2 * NTP) * 4, 4, gbands, tbl, (1 << W) + 1, stagger_cycles);
+  uint8_t* bands = tc_cta_begin<NTP>(c, smem, id, (2 * (dside_limbs<NTP>() / 4) + 2 * NTP) * 4, 4, gbands, tbl, (1 << W), stagger_cycles);
   for (long chunk = id.cta; chunk * id.nthr < batch; chunk += id.ncta) {
     long g[TC_RL]; bool store[TC_RL];
     tc_chunk_rows(id, chunk, batch, g, store);

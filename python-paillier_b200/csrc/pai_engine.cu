@@ -256,6 +256,16 @@ template <int W> struct BodyMaxThreads<TcPowBody<2, W>> { static const int v = 5
 template <int W> struct BodyMaxThreads<TcPowBody<4, W>> { static const int v = 512; };
 template <int W> struct BodyMaxThreads<TcStrausBody<2, W>> { static const int v = 512; };
 template <int W> struct BodyMaxThreads<TcStrausBody<4, W>> { static const int v = 512; };
+// 192 / 256 digits: THREE groups (384 threads, 168 registers) once the high digit x1 lives in the thread's table strip in
+// L2 instead of shared memory; at 256 digits they share the two 256-column TMEM accumulators (taken per reduction)
+template <int W> struct BodyMaxThreads<TcDecBody<6, W>> { static const int v = 384; };
+template <int W> struct BodyMaxThreads<TcDecBody<8, W>> { static const int v = 384; };
+template <> struct BodyMaxThreads<TcEncBody<6>> { static const int v = 384; };
+template <> struct BodyMaxThreads<TcEncBody<8>> { static const int v = 384; };
+template <int W> struct BodyMaxThreads<TcPowBody<6, W>> { static const int v = 384; };
+template <int W> struct BodyMaxThreads<TcPowBody<8, W>> { static const int v = 384; };
+template <int W> struct BodyMaxThreads<TcStrausBody<6, W>> { static const int v = 384; };
+template <int W> struct BodyMaxThreads<TcStrausBody<8, W>> { static const int v = 384; };
 }  // namespace pai
 #endif
 namespace {
@@ -723,7 +733,9 @@ int do_encrypt_digit(pai_pub* k, const uint32_t* m_, const uint32_t* r, uint32_t
   return rt_launch(body, g.grid, g.nthr, g.smem, s);
 }
 
-// launch geometry of a tensor-core kernel: 2 groups of 128 threads per CTA when shared memory allows, else 1
+// launch geometry of a tensor-core kernel: as many 128-thread groups per CTA as the body's register budget
+// (BodyMaxThreads), shared memory (tc_x1_global decides where the high digit lives) and the TMEM accumulator slots allow.
+// PAI_TC_GROUPS=<n> caps the group count (experiments).
 template <class B, int NTH, class SmemFn>
 int tc_geometry_of(int device, SmemFn smem_bytes, long batch, Geom& g) {
 #if defined(PAI_HOSTSIM)
@@ -735,16 +747,26 @@ int tc_geometry_of(int device, SmemFn smem_bytes, long batch, Geom& g) {
   return 0;
 #else
   const size_t max_smem = rt_max_smem(device);
-  for (int nthr = 4 * TC_M; nthr >= TC_M; nthr /= 2) {                      // 4, 2 or 1 groups of 128 threads
-    if (nthr > BodyMaxThreads<B>::v) continue;
+  const char* eg = getenv("PAI_TC_GROUPS");
+  const int want_groups = eg && *eg ? atoi(eg) : 0;
+  for (int groups = 4; groups >= 1; groups--) {
+    const int nthr = groups * TC_M;
+    if (nthr > BodyMaxThreads<B>::v || (want_groups && groups > want_groups)) continue;
+    if (groups > tc_tmem_slots(NTH) && tc_tmem_slots(NTH) < 2) continue;          // sharing needs at least two slots
     size_t smem = smem_bytes(nthr);
-    if (smem + 64 > max_smem || (nthr / TC_M) * 32 * NTH > 512) continue;      // shared memory, TMEM columns
+    if (smem + 128 > max_smem) continue;
     int occ = rt_occupancy<B>(nthr, smem);
     if (occ <= 0) continue;
-    occ = std::min(occ, 512 / tc_tmem_cols<NTH>(nthr / TC_M));     // TMEM columns of the SM
-    long chunks = (batch + nthr - 1) / nthr;
-    g.nthr = nthr; g.smem = smem;
-    g.grid = (int)std::max(1L, std::min(chunks, (long)rt_sm_count(device) * occ));
+    occ = std::min(occ, std::max(1, 512 / tc_tmem_cols<NTH>(groups)));            // TMEM columns of the SM
+    const long slots = (long)rt_sm_count(device) * occ;
+    int use = groups;
+    // less than one wave of rows (a small batch, or the tail the callers split off): the fewest groups per CTA that still
+    // hold it in one wave -- a group sharing its SM with fewer others runs faster, and more SMs are busy
+    if (!want_groups) while (use > 1 && (long)(use - 1) * TC_M * slots >= batch) use--;
+    g.nthr = use * TC_M;
+    g.smem = smem_bytes(g.nthr);
+    long chunks = (batch + g.nthr - 1) / g.nthr;
+    g.grid = (int)std::max(1L, std::min(chunks, slots));
     return 0;
   }
   g_err = "tensor-core kernel cannot be resident";
@@ -760,9 +782,18 @@ int do_encrypt_tc(pai_pub* k, const uint32_t* m_, const uint32_t* r, uint32_t* c
   typedef TcEncBody<NTH> B;
   pai_mod* m = k->nmod;
   Geom g;
-  int rc = tc_geometry<NTH>(k, batch, g);
+  int rc = tc_geometry<NTH>(k, 1L << 40, g);
   if (rc) return rc;
-  rc = m->ws.get(s).tbl.ensure((size_t)g.grid * (size_t)(k->nodd + 2) * 4 * NTH * g.nthr * 16);
+  const long wave = (long)g.grid * g.nthr;
+  if (batch > wave && batch % wave) {               // whole waves, then the tail with a geometry of its own (tc_geometry_of)
+    const long head = batch - batch % wave;
+    rc = do_encrypt_tc<NTH>(k, m_, r, c, head, s);
+    if (rc) return rc;
+    return do_encrypt_tc<NTH>(k, m_ + head * 8 * NTH, r + head * 8 * NTH, c + head * 16 * NTH, batch - head, s);
+  }
+  rc = tc_geometry<NTH>(k, batch, g);
+  if (rc) return rc;
+  rc = m->ws.get(s).tbl.ensure((size_t)g.grid * (size_t)(k->nodd + 3) * 4 * NTH * g.nthr * 16);
   if (rc) return rc;
   B body{k->d_enc_consts, dc_enc_limbs(NTH) / 4, k->d_prog, k->nops, k->nodd, m_, r, c, batch, (u4*)m->ws.get(s).tbl.p,
          m->d_blob + dc_zero_offset(NTH), k->d_tc, k->tc_stagger, nullptr};
@@ -795,7 +826,7 @@ int do_powmod_tc(pai_pub* k, const uint32_t* base, const uint32_t* d_exp, int ex
   Geom g;
   int rc = tc_geometry_of<B, NTH>(m->device, [](int nthr) { return tc_pow_smem_bytes<NTH>(nthr); }, batch, g);
   if (rc) return rc;
-  rc = m->ws.get(s).tbl.ensure((size_t)g.grid * (((size_t)1 << W_VAR) + 1) * 4 * NTH * g.nthr * 16);
+  rc = m->ws.get(s).tbl.ensure((size_t)g.grid * (((size_t)1 << W_VAR) + 2) * 4 * NTH * g.nthr * 16);
   if (rc) return rc;
   B body{k->d_enc_consts, dc_pow_limbs(NTH) / 4, base, d_exp, exp_limbs, out, batch, (u4*)m->ws.get(s).tbl.p,
          m->d_blob + dc_zero_offset(NTH), k->d_tc, k->tc_stagger};
@@ -817,7 +848,7 @@ int do_straus_tc(pai_pub* k, const uint32_t* base, const uint32_t* d_exp, int ex
   const long ngroups = (batch + gsz - 1) / gsz;
   rc = tc_geometry_of<B, NTH>(m->device, [](int nthr) { return tc_pow_smem_bytes<NTH>(nthr); }, ngroups, g);
   if (rc) return rc;
-  rc = m->ws.get(s).tbl.ensure((size_t)g.grid * (((size_t)gsz << W_VAR) + 2) * 4 * NTH * g.nthr * 16);
+  rc = m->ws.get(s).tbl.ensure((size_t)g.grid * (((size_t)gsz << W_VAR) + 3) * 4 * NTH * g.nthr * 16);
   if (rc) return rc;
   B body{k->d_enc_consts, dc_pow_limbs(NTH) / 4, base, d_exp, exp_limbs, (int)gsz, partial, batch, (u4*)m->ws.get(s).tbl.p,
          m->d_blob + dc_zero_offset(NTH), k->d_tc, k->tc_stagger};
@@ -911,9 +942,18 @@ template <int NTP>
 int do_decrypt_tc(pai_priv* k, const uint32_t* c, uint32_t* out, long batch, rt_stream s) {
   typedef TcDecBody<NTP, W_DEC> B;
   Geom g;
-  int rc = tc_dec_geometry<NTP>(k, batch, g);
+  int rc = tc_dec_geometry<NTP>(k, 1L << 40, g);
   if (rc) return rc;
-  rc = k->ws.get(s).tbl.ensure((size_t)g.grid * (((size_t)1 << W_DEC) + 1) * 4 * NTP * g.nthr * 16);
+  const long wave = (long)g.grid * g.nthr;
+  if (batch > wave && batch % wave) {               // whole waves, then the tail with a geometry of its own (tc_geometry_of)
+    const long head = batch - batch % wave;
+    rc = do_decrypt_tc<NTP>(k, c, out, head, s);
+    if (rc) return rc;
+    return do_decrypt_tc<NTP>(k, c + head * 32 * NTP, out + head * 16 * NTP, batch - head, s);
+  }
+  rc = tc_dec_geometry<NTP>(k, batch, g);
+  if (rc) return rc;
+  rc = k->ws.get(s).tbl.ensure((size_t)g.grid * (((size_t)1 << W_DEC) + 2) * 4 * NTP * g.nthr * 16);
   if (rc) return rc;
   int cq = 2 * (dside_limbs<NTP>() / 4) + 2 * NTP;
   B body{k->d_dconsts, cq, k->nwin_p, k->nwin_q, c, out, batch, (u4*)k->ws.get(s).tbl.p, k->d_tc, k->tc_stagger};

@@ -84,7 +84,9 @@ PAI_DEV void tc_setup(const uint32_t* N, uint8_t* blob, uint32_t* scratch) {
 template <int NTH>
 struct TcCtx {
   DigitEnv* dc;
-  u4* H[2];                 // shared half-buffers, interleaved: quad q of thread t at H[i][q * nthr + t]
+  u4* X;                    // shared half-buffer of the low digit x0, interleaved: quad q of thread t at X[q * nthr + t]
+  Opnd H1;                  // half-buffer of the high digit x1 of row 0 / this thread: shared (stride nthr) when it fits next
+                            // to X for the number of groups wanted, else a slot of the thread's table strip in global memory
   u4* A;                    // this group's operand buffer (128 * D bytes, tc_a_off layout)
   const uint8_t* band[2];   // shared: band(N'), band(n)
   Opnd tbl;                 // window table of THIS thread (global, stride nthr); simulation: of row 0
@@ -94,7 +96,12 @@ struct TcCtx {
 #if defined(PAI_HOSTSIM)
   int32_t tmem[TC_RL][512];
 #else
-  uint32_t tmem;            // TMEM address of this group's accumulator (lane 0, first column)
+  uint32_t tmem;            // TMEM address of the accumulator this group currently uses (lane 0, first column)
+  uint32_t tmem_base;       // first column of the CTA's TMEM allocation
+  int nslots;               // accumulator slots of D columns in it; groups > nslots: slots are taken per reduction
+  uint32_t* locks;          // shared: one word per slot (0 free / 1 taken) followed by one slot-index word per group
+  int slot;                 // slot held (static assignment: the group index)
+  int ngroups;
   uint64_t* mbar;           // the group's mbarrier
   uint32_t phase;
   int grp;                  // group index (named barrier 1 + grp)
@@ -111,8 +118,19 @@ struct TcCtx {
 #define TC_PROF(c, t, i) (void)0
 #endif
 
+// Where the high digit x1 of the running value lives.  Shared memory next to x0 wherever that does not cost a group of
+// the CTA; at 192 and 256 digits (1536/2048-bit n, the primes of 3072/4096-bit keys) a third group only fits when x1 moves
+// to the thread's table strip in global memory (L2-resident: 256 B per thread), and the third group is worth more.
 template <int NTH>
-PAI_DEV Opnd tc_h(const TcCtx<NTH>& c, int i, int rw) { Opnd o; o.p = c.H[i] + c.tid + rw; o.s = c.nthr; return o; }
+PAI_HD constexpr bool tc_x1_global() { return NTH == 6 || NTH == 8; }
+
+template <int NTH>
+PAI_DEV Opnd tc_h(const TcCtx<NTH>& c, int i, int rw) {
+  Opnd o;
+  if (i == 0) { o.p = c.X + c.tid + rw; o.s = c.nthr; }
+  else { o.p = c.H1.p + rw; o.s = c.H1.s; }
+  return o;
+}
 template <int NTH>
 PAI_DEV Opnd tc_a(const TcCtx<NTH>& c, int rw) {
   const int r = c.row0 + rw;
@@ -125,7 +143,13 @@ PAI_DEV Opnd tc_tbl(const TcCtx<NTH>& c, int e, int half, int rw) {
 template <int NTH>
 PAI_DEV Opnd tc_park(const TcCtx<NTH>& c, int rw) { return tc_tbl<NTH>(c, c.slots, 0, rw); }
 template <int NTH>
-PAI_DEV SOpnd tc_hs(const TcCtx<NTH>& c, int i, int rw) { return to_shared(tc_h<NTH>(c, i, rw)); }
+PAI_DEV SOpnd tc_xs(const TcCtx<NTH>& c, int rw) { return to_shared(tc_h<NTH>(c, 0, rw)); }
+// x1 as the operand type of its home: shared-memory loads where it is in shared memory
+template <int NTH>
+PAI_DEV auto tc_x1(const TcCtx<NTH>& c, int rw) {
+  if constexpr (tc_x1_global<NTH>()) return tc_h<NTH>(c, 1, rw);
+  else return to_shared(tc_h<NTH>(c, 1, rw));
+}
 template <int NTH>
 PAI_DEV SOpnd tc_as(const TcCtx<NTH>& c, int rw) { return to_shared(tc_a<NTH>(c, rw)); }
 
@@ -217,7 +241,21 @@ PAI_DEV void tc_gemm(TcCtx<NTH>& c, int which) {
 #else
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy writes of A -> tensor-core reads
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");    // our tcgen05.ld of the previous accumulator are done
+  if (which == 0 && c.ngroups > c.nslots) {
+    // more groups than accumulator slots (three groups, two 256-column slots at 2048-bit keys): a group holds a slot
+    // from the first GEMM of a reduction to the end of its second epilogue -- about a third of its time
+    if (c.row0 == 0) {
+      int sl = c.grp % c.nslots;
+      while (atomicCAS(&c.locks[sl], 0u, 1u) != 0u) { sl = sl + 1 == c.nslots ? 0 : sl + 1; __nanosleep(100); }
+      __threadfence_block();
+      c.locks[4 + c.grp] = (uint32_t)sl;
+    }
+  }
   tc_bar_sync(1 + c.grp, TC_M);
+  if (which == 0 && c.ngroups > c.nslots) {
+    c.slot = (int)((volatile uint32_t*)c.locks)[4 + c.grp];
+    c.tmem = c.tmem_base + (uint32_t)(c.slot * D);
+  }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (c.row0 == 0) {
     // Both Toeplitz operands are triangular: digit block kappa of A reaches only the columns j >= 32 kappa of A x T(N')
@@ -248,6 +286,20 @@ PAI_DEV void tc_gemm(TcCtx<NTH>& c, int which) {
   tc_mbar_wait(c.mbar, c.phase);
   c.phase ^= 1u;
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#endif
+}
+
+// end of a reduction: the group is done reading its accumulator; with more groups than slots the slot is handed back
+template <int NTH>
+PAI_DEV void tc_tmem_release(TcCtx<NTH>& c) {
+#if !defined(PAI_HOSTSIM)
+  if (c.ngroups > c.nslots) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tc_bar_sync(1 + c.grp, TC_M);
+    if (c.row0 == 0) { __threadfence_block(); atomicExch(&c.locks[c.slot], 0u); }
+  }
+#else
+  (void)c;
 #endif
 }
 
@@ -483,8 +535,8 @@ PAI_FN void tc_epi_t(const TcCtx<NTH>* c, int rw, SOpnd A, Opnd Ag, Opnd P, cons
 }
 
 // P2 (multiplication): B = x0*y1 + x1*y0 + W;  B_lo -> A (over W), B_hi (+ wtop + [B_lo != 0]) -> bh
-template <int NTH, class XT>
-PAI_FN void tc_prod2_mul(SOpnd A, SOpnd bh, XT x0, XT x1, Opnd y0, Opnd y1, TcRow* st) {
+template <int NTH, class XT, class X1T>
+PAI_FN void tc_prod2_mul(SOpnd A, SOpnd bh, XT x0, X1T x1, Opnd y0, Opnd y1, TcRow* st) {
   Acc acc;
   acc_clear(acc);
   TcLow low; low.lowor = 0; low.top = 0;
@@ -495,15 +547,29 @@ PAI_FN void tc_prod2_mul(SOpnd A, SOpnd bh, XT x0, XT x1, Opnd y0, Opnd y1, TcRo
     uint32_t yn1[8], yn0[8];                             // table tiles requested one iteration ahead (L2 latency)
     ld_tile(y1, k - lo, yn1);
     ld_tile(y0, k - lo, yn0);
-    for (int i = lo; i <= hi; i++) {
-      uint32_t x[8], ya[8], yb[8];
-      PAI_UNROLL
-      for (int j = 0; j < 8; j++) { ya[j] = yn1[j]; yb[j] = yn0[j]; }
-      if (i < hi) { ld_tile(y1, k - i - 1, yn1); ld_tile(y0, k - i - 1, yn0); }
-      ld_tile(x0, i, x);
-      tile_mac(acc, x, ya);
-      ld_tile(x1, i, x);
-      tile_mac(acc, x, yb);
+    if constexpr (tc_x1_global<NTH>()) {                 // ... and so are x1's when it lives in global memory
+      uint32_t xn1[8];
+      ld_tile(x1, lo, xn1);
+      for (int i = lo; i <= hi; i++) {
+        uint32_t x[8], xb[8], ya[8], yb[8];
+        PAI_UNROLL
+        for (int j = 0; j < 8; j++) { ya[j] = yn1[j]; yb[j] = yn0[j]; xb[j] = xn1[j]; }
+        if (i < hi) { ld_tile(y1, k - i - 1, yn1); ld_tile(y0, k - i - 1, yn0); ld_tile(x1, i + 1, xn1); }
+        ld_tile(x0, i, x);
+        tile_mac(acc, x, ya);
+        tile_mac(acc, xb, yb);
+      }
+    } else {
+      for (int i = lo; i <= hi; i++) {
+        uint32_t x[8], ya[8], yb[8];
+        PAI_UNROLL
+        for (int j = 0; j < 8; j++) { ya[j] = yn1[j]; yb[j] = yn0[j]; }
+        if (i < hi) { ld_tile(y1, k - i - 1, yn1); ld_tile(y0, k - i - 1, yn0); }
+        ld_tile(x0, i, x);
+        tile_mac(acc, x, ya);
+        ld_tile(x1, i, x);
+        tile_mac(acc, x, yb);
+      }
     }
     uint32_t v[8];
     if (k < NTH) {
@@ -527,8 +593,8 @@ PAI_FN void tc_prod2_mul(SOpnd A, SOpnd bh, XT x0, XT x1, Opnd y0, Opnd y1, TcRo
 // P2 (squaring): B = 2*x0*x1 + W.  x1 is dead after this phase, so it is doubled IN PLACE first (x1' = 2*x1 mod R, top bit
 // tb) and the cross products run as a plain product x0 * x1' in one accumulator; tb * x0 * R enters as x0's tiles in the
 // upper columns (each read right before B_hi overwrites it).
-template <int NTH>
-PAI_FN void tc_prod2_sqr(SOpnd A, SOpnd bh, SOpnd x0, SOpnd x1, TcRow* st) {
+template <int NTH, class X1T>
+PAI_FN void tc_prod2_sqr(SOpnd A, SOpnd bh, SOpnd x0, X1T x1, TcRow* st) {
   uint32_t tb = 0;
   for (int t = 0; t < NTH; t++) {
     uint32_t x[8], y[8];
@@ -546,10 +612,23 @@ PAI_FN void tc_prod2_sqr(SOpnd A, SOpnd bh, SOpnd x0, SOpnd x1, TcRow* st) {
   for (int k = 0; k < 2 * NTH; k++) {
     int lo = k - NTH + 1 > 0 ? k - NTH + 1 : 0;
     int hc = k < NTH ? k : NTH - 1;
-    for (int i = lo; i <= hc; i++) {
-      uint32_t x[8], y[8];
-      ld_tile(x0, i, x); ld_tile(x1, k - i, y);
-      tile_mac(acc, x, y);
+    if constexpr (tc_x1_global<NTH>()) {                 // x1 in global memory: next tile requested one product ahead
+      uint32_t yn[8];
+      ld_tile(x1, k - lo, yn);
+      for (int i = lo; i <= hc; i++) {
+        uint32_t x[8], y[8];
+        PAI_UNROLL
+        for (int j = 0; j < 8; j++) y[j] = yn[j];
+        if (i < hc) ld_tile(x1, k - i - 1, yn);
+        ld_tile(x0, i, x);
+        tile_mac(acc, x, y);
+      }
+    } else {
+      for (int i = lo; i <= hc; i++) {
+        uint32_t x[8], y[8];
+        ld_tile(x0, i, x); ld_tile(x1, k - i, y);
+        tile_mac(acc, x, y);
+      }
     }
     uint32_t v[8];
     if (k < NTH) {
@@ -617,11 +696,12 @@ PAI_FN void tc_z0_copy(SOpnd dst, Opnd P, Opnd N, uint32_t mask) {
 }
 
 // ---- one product, all phases.  Operand resolvers map a row to its operand (rows differ only in their base address):
-//   x0, x1: digits of the first factor (shared half-buffers, or generic operands for rows read straight from global
-//   memory); y0, y1: digits of the second factor (generic; ignored for SQR);  bhi: index of the half-buffer where Z1 is
-//   built (may be x0's: its tiles are dead when they are overwritten);  z0i: the half-buffer that receives Z0.
+//   x0: low digit of the first factor (the shared buffer X, or a generic operand for rows read straight from global
+//   memory); x1: its high digit (generic); y0, y1: digits of the second factor (generic; ignored for SQR).
+//   Result: Z0 in X (buffer 0), Z1 in buffer 1 -- Z1 is built in X (over x0, whose tiles are dead by then), moved to
+//   buffer 1 at the end, and Z0 = t - n*carry comes in from the park slot.
 template <int NTH, bool SQR, class FX0, class FX1, class FY0, class FY1>
-PAI_DEV void tc_op(TcCtx<NTH>& c, FX0 x0, FX1 x1, FY0 y0, FY1 y1, int bhi, int z0i) {
+PAI_DEV void tc_op(TcCtx<NTH>& c, FX0 x0, FX1 x1, FY0 y0, FY1 y1) {
   TcRow st[TC_RL];
   TC_PROF_START(c, t0);
   TC_EACH_ROW {
@@ -637,10 +717,11 @@ PAI_DEV void tc_op(TcCtx<NTH>& c, FX0 x0, FX1 x1, FY0 y0, FY1 y1, int bhi, int z
   tc_gemm<NTH>(c, 1);
   TC_PROF(c, t0, 3);
   TC_EACH_ROW tc_epi_t<NTH>(&c, rw, tc_as<NTH>(c, rw), tc_a<NTH>(c, rw), tc_park<NTH>(c, rw), c.dc, &st[rw]);
+  tc_tmem_release<NTH>(c);
   TC_PROF(c, t0, 4);
   TC_EACH_ROW {
-    if constexpr (SQR) tc_prod2_sqr<NTH>(tc_as<NTH>(c, rw), tc_hs<NTH>(c, bhi, rw), x0(rw), x1(rw), &st[rw]);
-    else tc_prod2_mul<NTH>(tc_as<NTH>(c, rw), tc_hs<NTH>(c, bhi, rw), x0(rw), x1(rw), y0(rw), y1(rw), &st[rw]);
+    if constexpr (SQR) tc_prod2_sqr<NTH>(tc_as<NTH>(c, rw), tc_xs<NTH>(c, rw), x0(rw), x1(rw), &st[rw]);
+    else tc_prod2_mul<NTH>(tc_as<NTH>(c, rw), tc_xs<NTH>(c, rw), x0(rw), x1(rw), y0(rw), y1(rw), &st[rw]);
   }
   TC_PROF(c, t0, SQR ? 5 : 9);
   tc_gemm<NTH>(c, 0);
@@ -649,174 +730,171 @@ PAI_DEV void tc_op(TcCtx<NTH>& c, FX0 x0, FX1 x1, FY0 y0, FY1 y1, int bhi, int z
   TC_PROF(c, t0, 2);
   tc_gemm<NTH>(c, 1);
   TC_PROF(c, t0, 3);
-  TC_EACH_ROW tc_epi_z<NTH>(&c, rw, tc_as<NTH>(c, rw), tc_hs<NTH>(c, bhi, rw), tc_h<NTH>(c, bhi, rw), c.dc, &st[rw]);
+  TC_EACH_ROW tc_epi_z<NTH>(&c, rw, tc_as<NTH>(c, rw), tc_xs<NTH>(c, rw), tc_h<NTH>(c, 0, rw), c.dc, &st[rw]);
+  tc_tmem_release<NTH>(c);
   TC_PROF(c, t0, 6);
-  TC_EACH_ROW tc_z0_copy<NTH>(tc_hs<NTH>(c, z0i, rw), tc_park<NTH>(c, rw), c.dc->N, 0u - st[rw].carry);
+  TC_EACH_ROW {
+    big_copy<NTH>(tc_h<NTH>(c, 1, rw), tc_h<NTH>(c, 0, rw));                                     // Z1 -> buffer 1
+    tc_z0_copy<NTH>(tc_xs<NTH>(c, rw), tc_park<NTH>(c, rw), c.dc->N, 0u - st[rw].carry);        // Z0 -> X
+  }
   TC_PROF(c, t0, 7);
 #if !defined(PAI_HOSTSIM)
   if (c.prof && (threadIdx.x & 31) == 0) c.prof[SQR ? 10 : 11] += 1;
 #endif
 }
 
-// in-place forms on the two shared half-buffers: x0 in H[a], x1 in H[1-a]  ->  Z1 in H[a], Z0 in H[1-a]; the caller flips a
+// in-place forms: (x0, x1) in buffers (0, 1)  ->  (Z0, Z1) in buffers (0, 1)
 template <int NTH>
-PAI_DEV void tc_sqr_inplace(TcCtx<NTH>& c, int a) {
-  auto X = [&](int rw) { return tc_hs<NTH>(c, a, rw); };
-  auto Y = [&](int rw) { return tc_hs<NTH>(c, a ^ 1, rw); };
-  auto G = [&](int rw) { return tc_h<NTH>(c, a, rw); };
-  tc_op<NTH, true>(c, X, Y, G, G, a, a ^ 1);
+PAI_DEV void tc_sqr_inplace(TcCtx<NTH>& c) {
+  auto X = [&](int rw) { return tc_xs<NTH>(c, rw); };
+  auto Y = [&](int rw) { return tc_x1<NTH>(c, rw); };
+  auto G = [&](int rw) { return tc_h<NTH>(c, 1, rw); };
+  tc_op<NTH, true>(c, X, Y, G, G);
 }
 template <int NTH, class FY0, class FY1>
-PAI_DEV void tc_mul_inplace(TcCtx<NTH>& c, int a, FY0 y0, FY1 y1) {
-  auto X = [&](int rw) { return tc_hs<NTH>(c, a, rw); };
-  auto Y = [&](int rw) { return tc_hs<NTH>(c, a ^ 1, rw); };
-  tc_op<NTH, false>(c, X, Y, y0, y1, a, a ^ 1);
+PAI_DEV void tc_mul_inplace(TcCtx<NTH>& c, FY0 y0, FY1 y1) {
+  auto X = [&](int rw) { return tc_xs<NTH>(c, rw); };
+  auto Y = [&](int rw) { return tc_x1<NTH>(c, rw); };
+  tc_op<NTH, false>(c, X, Y, y0, y1);
 }
 template <int NTH>
-PAI_DEV void tc_tbl_store(TcCtx<NTH>& c, int e, int a) {          // T[e] = (H[a], H[1-a])
+PAI_DEV void tc_tbl_store(TcCtx<NTH>& c, int e) {                 // T[e] = (buffer 0, buffer 1)
   TC_EACH_ROW {
-    big_copy<NTH>(tc_tbl<NTH>(c, e, 0, rw), tc_h<NTH>(c, a, rw));
-    big_copy<NTH>(tc_tbl<NTH>(c, e, 1, rw), tc_h<NTH>(c, a ^ 1, rw));
+    big_copy<NTH>(tc_tbl<NTH>(c, e, 0, rw), tc_h<NTH>(c, 0, rw));
+    big_copy<NTH>(tc_tbl<NTH>(c, e, 1, rw), tc_h<NTH>(c, 1, rw));
   }
 }
 template <int NTH>
-PAI_DEV void tc_tbl_load(TcCtx<NTH>& c, int e, int a) {           // (H[a], H[1-a]) = T[e]
+PAI_DEV void tc_tbl_load(TcCtx<NTH>& c, int e) {                  // (buffer 0, buffer 1) = T[e]
   TC_EACH_ROW {
-    big_copy<NTH>(tc_h<NTH>(c, a, rw), tc_tbl<NTH>(c, e, 0, rw));
-    big_copy<NTH>(tc_h<NTH>(c, a ^ 1, rw), tc_tbl<NTH>(c, e, 1, rw));
+    big_copy<NTH>(tc_h<NTH>(c, 0, rw), tc_tbl<NTH>(c, e, 0, rw));
+    big_copy<NTH>(tc_h<NTH>(c, 1, rw), tc_tbl<NTH>(c, e, 1, rw));
   }
+}
+template <int NTH>
+PAI_DEV void tc_set_one(TcCtx<NTH>& c) {                          // (buffer 0, buffer 1) = Montgomery one
+  TC_EACH_ROW { big_copy<NTH>(tc_h<NTH>(c, 0, rw), c.dc->ONEM.d0); big_copy<NTH>(tc_h<NTH>(c, 1, rw), c.dc->ONEM.d1); }
 }
 
-// Sliding-window exponentiation with the host-built program (see dpow_prog): base in (H[a], H[1-a]); returns the new a.
+// Sliding-window exponentiation with the host-built program (see dpow_prog): base in buffers (0, 1), result likewise.
 template <int NTH>
-PAI_DEV int tc_pow_prog(TcCtx<NTH>& c, int a, const uint32_t* prog, int nops, int nodd) {
-  tc_tbl_store<NTH>(c, 0, a);                                             // T[0] = base
+PAI_DEV void tc_pow_prog(TcCtx<NTH>& c, const uint32_t* prog, int nops, int nodd) {
+  tc_tbl_store<NTH>(c, 0);                                                // T[0] = base
   if (nodd > 1) {
-    tc_sqr_inplace<NTH>(c, a); a ^= 1;
-    tc_tbl_store<NTH>(c, nodd, a);                                        // base^2
-    tc_tbl_load<NTH>(c, 0, a);
+    tc_sqr_inplace<NTH>(c);
+    tc_tbl_store<NTH>(c, nodd);                                           // base^2
+    tc_tbl_load<NTH>(c, 0);
     for (int k = 1; k < nodd; k++) {                                      // T[k] = T[k-1] * base^2
-      tc_mul_inplace<NTH>(c, a, [&](int rw) { return tc_tbl<NTH>(c, nodd, 0, rw); }, [&](int rw) { return tc_tbl<NTH>(c, nodd, 1, rw); });
-      a ^= 1;
-      tc_tbl_store<NTH>(c, k, a);
+      tc_mul_inplace<NTH>(c, [&](int rw) { return tc_tbl<NTH>(c, nodd, 0, rw); }, [&](int rw) { return tc_tbl<NTH>(c, nodd, 1, rw); });
+      tc_tbl_store<NTH>(c, k);
     }
   }
-  tc_tbl_load<NTH>(c, (int)(prog[0] & 0xffffu), a);
+  tc_tbl_load<NTH>(c, (int)(prog[0] & 0xffffu));
   for (int i = 1; i < nops; i++) {
     const uint32_t op = prog[i];
     const int nsq = (int)(op >> 16), idx = (int)(op & 0xffffu);
-    for (int s = 0; s < nsq; s++) { tc_sqr_inplace<NTH>(c, a); a ^= 1; }
-    if (idx != 0xffff) {
-      tc_mul_inplace<NTH>(c, a, [&](int rw) { return tc_tbl<NTH>(c, idx, 0, rw); }, [&](int rw) { return tc_tbl<NTH>(c, idx, 1, rw); });
-      a ^= 1;
-    }
+    for (int s = 0; s < nsq; s++) tc_sqr_inplace<NTH>(c);
+    if (idx != 0xffff)
+      tc_mul_inplace<NTH>(c, [&](int rw) { return tc_tbl<NTH>(c, idx, 0, rw); }, [&](int rw) { return tc_tbl<NTH>(c, idx, 1, rw); });
   }
-  return a;
+}
+
+// plain number Z0 + n*Z1 of the digits in buffers (0, 1) -> out_row(rw) (a scratch table entry for padding rows)
+template <int NTH, class FOUT>
+PAI_DEV void tc_store_plain(TcCtx<NTH>& c, FOUT out_row, const bool* store) {
+  TC_EACH_ROW {
+    DNum z; z.d0 = tc_h<NTH>(c, 0, rw); z.d1 = tc_h<NTH>(c, 1, rw);
+    Opnd o;
+    if (store[rw]) { o.p = (u4*)out_row(rw); o.s = 1; }
+    else o = tc_tbl<NTH>(c, 0, 0, rw);                                   // scratch: table entry 0 (2*NTH tiles)
+    digits_to_plain<NTH>(o, z, c.dc->N);
+  }
 }
 
 // raw_encrypt (phe/paillier.py:102-139) for the rows of one group: c = (1 + n*m) * r^n mod n^2.
-//   rows: global row index of every row of the group (clamped to batch - 1), store: whether it is a real row.
+//   g: global row index of every row of the group (clamped to batch - 1), store: whether it is a real row.
 template <int NTH>
 PAI_DEV void tc_encrypt_rows(TcCtx<NTH>& c, const uint32_t* prog, int nops, int nodd, const uint32_t* m, const uint32_t* r,
                              uint32_t* out, const long* g, const bool* store) {
   const DigitEnv& dc = *c.dc;
   const int ln = 8 * NTH, lc = 16 * NTH;
-  // (r, 0) * RR: enter the Montgomery domain; Z1 -> H[0], Z0 -> H[1]
+  // (r, 0) * RR: enter the Montgomery domain
   tc_op<NTH, false>(
       c, [&](int rw) { Opnd o; o.p = (u4*)(r + g[rw] * ln); o.s = 1; return o; }, [&](int) { return dc.ZERO; },
-      [&](int) { return dc.RR.d0; }, [&](int) { return dc.RR.d1; }, 0, 1);
-  int a = 1;
-  if (nops <= 0) {                                                        // exponent 0 -> Montgomery one
-    TC_EACH_ROW { big_copy<NTH>(tc_h<NTH>(c, a, rw), dc.ONEM.d0); big_copy<NTH>(tc_h<NTH>(c, a ^ 1, rw), dc.ONEM.d1); }
-  } else {
-    a = tc_pow_prog<NTH>(c, a, prog, nops, nodd);
-  }
+      [&](int) { return dc.RR.d0; }, [&](int) { return dc.RR.d1; });
+  if (nops <= 0) tc_set_one<NTH>(c);                                      // exponent 0 -> Montgomery one
+  else tc_pow_prog<NTH>(c, prog, nops, nodd);
   // times the PLAIN digit pair (1, m) of the nude ciphertext 1 + n*m: leaves the domain
-  tc_mul_inplace<NTH>(c, a, [&](int) { return dc.ONE; }, [&](int rw) { Opnd o; o.p = (u4*)(m + g[rw] * ln); o.s = 1; return o; });
-  a ^= 1;
-  TC_EACH_ROW {
-    DNum z; z.d0 = tc_h<NTH>(c, a, rw); z.d1 = tc_h<NTH>(c, a ^ 1, rw);
-    Opnd o;
-    if (store[rw]) { o.p = (u4*)(out + g[rw] * lc); o.s = 1; }
-    else o = tc_tbl<NTH>(c, 0, 0, rw);                                   // scratch: table entry 0 (2*NTH tiles)
-    digits_to_plain<NTH>(o, z, dc.N);
-  }
+  tc_mul_inplace<NTH>(c, [&](int) { return dc.ONE; }, [&](int rw) { Opnd o; o.p = (u4*)(m + g[rw] * ln); o.s = 1; return o; });
+  tc_store_plain<NTH>(c, [&](int rw) { return out + g[rw] * lc; }, store);
 }
 
 // ------------------------------------------------------------------------------------------------
-// raw_decrypt with CRT (phe/paillier.py:328-374) on the tensor-core path: the same program as prog_decrypt_digit
-// (pai_digit.cuh), every product modulo p^2 / q^2 through tc_op.  Fixed windows of W bits (secret exponent shared by
-// the batch: no digit is skipped); the 2^W-entry table lives in global memory, entry 2^W is the park slot.
-// table of powers of the base in (H[a], H[1-a]) at entries e0 .. e0 + 2^W - 1: T[0] = 1, T[1] = base, T[i] = T[i-1] * base
+// Fixed windows of W bits (secret exponent shared by the batch: no digit is skipped, or per-element exponents with a
+// group-uniform window count); the 2^W-entry tables live in global memory.
+// table of powers of the base in buffers (0, 1) at entries e0 .. e0 + 2^W - 1: T[0] = 1, T[1] = base, T[i] = T[i-1] * base
 template <int NTP, int W>
-PAI_DEV int tc_build_table(TcCtx<NTP>& c, int a, int e0) {
+PAI_DEV void tc_build_table(TcCtx<NTP>& c, int e0) {
   const DigitEnv& dc = *c.dc;
   TC_EACH_ROW { big_copy<NTP>(tc_tbl<NTP>(c, e0, 0, rw), dc.ONEM.d0); big_copy<NTP>(tc_tbl<NTP>(c, e0, 1, rw), dc.ONEM.d1); }
-  tc_tbl_store<NTP>(c, e0 + 1, a);
-  tc_sqr_inplace<NTP>(c, a); a ^= 1;
-  tc_tbl_store<NTP>(c, e0 + 2, a);
+  tc_tbl_store<NTP>(c, e0 + 1);
+  tc_sqr_inplace<NTP>(c);
+  tc_tbl_store<NTP>(c, e0 + 2);
   for (int i = 3; i < (1 << W); i++) {
-    tc_mul_inplace<NTP>(c, a, [&](int rw) { return tc_tbl<NTP>(c, e0 + 1, 0, rw); }, [&](int rw) { return tc_tbl<NTP>(c, e0 + 1, 1, rw); });
-    a ^= 1;
-    tc_tbl_store<NTP>(c, e0 + i, a);
+    tc_mul_inplace<NTP>(c, [&](int rw) { return tc_tbl<NTP>(c, e0 + 1, 0, rw); }, [&](int rw) { return tc_tbl<NTP>(c, e0 + 1, 1, rw); });
+    tc_tbl_store<NTP>(c, e0 + i);
   }
-  return a;
+}
+// (buffer 0, buffer 1) = entry e(rw) of the table, e differing per row
+template <int NTP, class FE>
+PAI_DEV void tc_tbl_load_f(TcCtx<NTP>& c, FE e) {
+  TC_EACH_ROW {
+    const int d = e(rw);
+    big_copy<NTP>(tc_h<NTP>(c, 0, rw), tc_tbl<NTP>(c, d, 0, rw));
+    big_copy<NTP>(tc_h<NTP>(c, 1, rw), tc_tbl<NTP>(c, d, 1, rw));
+  }
 }
 template <int NTP, int W, class FD>
-PAI_DEV int tc_pow_fixed_f(TcCtx<NTP>& c, int a, FD digit, int nwin) {          // digit(rw, window index) -> table entry of row rw
-  a = tc_build_table<NTP, W>(c, a, 0);
-  TC_EACH_ROW {
-    const int d = digit(rw, nwin - 1);
-    big_copy<NTP>(tc_h<NTP>(c, a, rw), tc_tbl<NTP>(c, d, 0, rw));
-    big_copy<NTP>(tc_h<NTP>(c, a ^ 1, rw), tc_tbl<NTP>(c, d, 1, rw));
-  }
+PAI_DEV void tc_pow_fixed_f(TcCtx<NTP>& c, FD digit, int nwin) {                // digit(rw, window index) -> table entry of row rw
+  tc_build_table<NTP, W>(c, 0);
+  tc_tbl_load_f<NTP>(c, [&](int rw) { return digit(rw, nwin - 1); });
   for (int wi = nwin - 2; wi >= 0; wi--) {
-    for (int s = 0; s < W; s++) { tc_sqr_inplace<NTP>(c, a); a ^= 1; }
-    tc_mul_inplace<NTP>(c, a, [&](int rw) { return tc_tbl<NTP>(c, digit(rw, wi), 0, rw); },
+    for (int s = 0; s < W; s++) tc_sqr_inplace<NTP>(c);
+    tc_mul_inplace<NTP>(c, [&](int rw) { return tc_tbl<NTP>(c, digit(rw, wi), 0, rw); },
                         [&](int rw) { return tc_tbl<NTP>(c, digit(rw, wi), 1, rw); });
-    a ^= 1;
   }
-  return a;
 }
 template <int NTP, int W>
-PAI_DEV int tc_pow_fixed(TcCtx<NTP>& c, int a, const uint32_t* e, int nl, int nwin) {
-  return tc_pow_fixed_f<NTP, W>(c, a, [&](int, int wi) { return (int)exp_digit(e, nl, wi * W, W); }, nwin);
+PAI_DEV void tc_pow_fixed(TcCtx<NTP>& c, const uint32_t* e, int nl, int nwin) {
+  tc_pow_fixed_f<NTP, W>(c, [&](int, int wi) { return (int)exp_digit(e, nl, wi * W, W); }, nwin);
 }
 
-// (H[0], H[1]) <- Montgomery digit form of the plain 2*NTH-tile numbers base_row(rw) = c_0 + c_1*R:
-// (c_0, 0) * R^2 + (c_1, 0) * R^3, accumulated in table entry `tmp`.  Returns a = 0.
+// buffers (0, 1) <- Montgomery digit form of the plain 2*NTH-tile numbers base_row(rw) = c_0 + c_1*R:
+// (c_0, 0) * R^2 + (c_1, 0) * R^3, accumulated in table entry `tmp`.
 template <int NTH, class FROW>
-PAI_DEV int tc_enter_wide(TcCtx<NTH>& c, FROW base_row, int tmp) {
+PAI_DEV void tc_enter_wide(TcCtx<NTH>& c, FROW base_row, int tmp) {
   const DigitEnv& dc = *c.dc;
   for (int i = 0; i < 2; i++) {
     const DNum E = i == 0 ? dc.RR : dc.E3;
     tc_op<NTH, false>(
         c, [&](int rw) { Opnd o; o.p = (u4*)(base_row(rw) + (size_t)i * 8 * NTH); o.s = 1; return o; }, [&](int) { return dc.ZERO; },
-        [&](int) { return E.d0; }, [&](int) { return E.d1; }, 0, 1);
-    if (i == 0) tc_tbl_store<NTH>(c, tmp, 1);
+        [&](int) { return E.d0; }, [&](int) { return E.d1; });
+    if (i == 0) tc_tbl_store<NTH>(c, tmp);
     else TC_EACH_ROW {
       DNum acc, add;
       acc.d0 = tc_tbl<NTH>(c, tmp, 0, rw); acc.d1 = tc_tbl<NTH>(c, tmp, 1, rw);
-      add.d0 = tc_h<NTH>(c, 1, rw); add.d1 = tc_h<NTH>(c, 0, rw);
+      add.d0 = tc_h<NTH>(c, 0, rw); add.d1 = tc_h<NTH>(c, 1, rw);
       dadd<NTH>(acc, add, dc.N);
     }
   }
-  tc_tbl_load<NTH>(c, tmp, 0);
-  return 0;
+  tc_tbl_load<NTH>(c, tmp);
 }
-// leave the domain and write the plain number Z0 + n*Z1 to out_row(rw) (a scratch table entry for padding rows)
+// leave the domain and write the plain number to out_row(rw)
 template <int NTH, class FOUT>
-PAI_DEV void tc_exit_plain(TcCtx<NTH>& c, int a, FOUT out_row, const bool* store) {
+PAI_DEV void tc_exit_plain(TcCtx<NTH>& c, FOUT out_row, const bool* store) {
   const DigitEnv& dc = *c.dc;
-  tc_mul_inplace<NTH>(c, a, [&](int) { return dc.ONE; }, [&](int) { return dc.ZERO; });
-  a ^= 1;
-  TC_EACH_ROW {
-    DNum z; z.d0 = tc_h<NTH>(c, a, rw); z.d1 = tc_h<NTH>(c, a ^ 1, rw);
-    Opnd o;
-    if (store[rw]) { o.p = (u4*)out_row(rw); o.s = 1; }
-    else o = tc_tbl<NTH>(c, 0, 0, rw);
-    digits_to_plain<NTH>(o, z, dc.N);
-  }
+  tc_mul_inplace<NTH>(c, [&](int) { return dc.ONE; }, [&](int) { return dc.ZERO; });
+  tc_store_plain<NTH>(c, out_row, store);
 }
 
 // c^k mod n^2 with per-element exponents (EncryptedNumber._raw_mul, phe/paillier.py:749-751) -- prog_powmod_digit on
@@ -824,26 +902,21 @@ PAI_DEV void tc_exit_plain(TcCtx<NTH>& c, int a, FOUT out_row, const bool* store
 template <int NTH, int W>
 PAI_DEV void tc_powmod_rows(TcCtx<NTH>& c, const uint32_t* base, const uint32_t* exp, int nl, int nwin, uint32_t* out,
                             const long* g, const bool* store) {
-  const DigitEnv& dc = *c.dc;
   const int lc = 16 * NTH;
-  int a = tc_enter_wide<NTH>(c, [&](int rw) { return base + g[rw] * lc; }, 0);
-  if (nwin <= 0) {
-    TC_EACH_ROW { big_copy<NTH>(tc_h<NTH>(c, a, rw), dc.ONEM.d0); big_copy<NTH>(tc_h<NTH>(c, a ^ 1, rw), dc.ONEM.d1); }
-  } else {
-    a = tc_pow_fixed_f<NTH, W>(c, a, [&](int rw, int wi) { return (int)exp_digit(exp + g[rw] * nl, nl, wi * W, W); }, nwin);
-  }
-  tc_exit_plain<NTH>(c, a, [&](int rw) { return out + g[rw] * lc; }, store);
+  tc_enter_wide<NTH>(c, [&](int rw) { return base + g[rw] * lc; }, 0);
+  if (nwin <= 0) tc_set_one<NTH>(c);
+  else tc_pow_fixed_f<NTH, W>(c, [&](int rw, int wi) { return (int)exp_digit(exp + g[rw] * nl, nl, wi * W, W); }, nwin);
+  tc_exit_plain<NTH>(c, [&](int rw) { return out + g[rw] * lc; }, store);
 }
 
 // prod_i c_i^(k_i) mod n^2 over the `gsz` elements of one row's group -- Straus' simultaneous exponentiation: one table of
 // 2^W powers per element, ONE chain of squarings shared by the whole group (the encrypted dot product of
 // examples/logistic_regression_encrypted_model.py:170-180 costs (2 + 2^W - 1 + nwin) products per element instead of
 // (2 + 2^W - 1 + nwin * (W + 1))).  Elements past the end of the batch count as exponent 0.  Table entries of element i:
-// 2^W * i ...; the two entries after the last table are the entry scratch and the park slot.
+// 2^W * i ...; the entry after the last table is the entry scratch (then the park slot and, maybe, buffer 1).
 template <int NTH, int W>
 PAI_DEV void tc_straus_rows(TcCtx<NTH>& c, const uint32_t* base, const uint32_t* exp, int nl, int gsz, int nwin, long batch,
                             uint32_t* out, const long* g, const bool* store) {
-  const DigitEnv& dc = *c.dc;
   const int lc = 16 * NTH;
   const int tmp = gsz << W;
   auto elem = [&](int rw, int i) { long j = g[rw] * gsz + i; return j < batch ? j : batch - 1; };
@@ -852,36 +925,30 @@ PAI_DEV void tc_straus_rows(TcCtx<NTH>& c, const uint32_t* base, const uint32_t*
     return j < batch ? (int)exp_digit(exp + j * nl, nl, wi * W, W) : 0;
   };
   for (int i = 0; i < gsz; i++) {
-    int a = tc_enter_wide<NTH>(c, [&](int rw) { return base + elem(rw, i) * lc; }, tmp);
-    tc_build_table<NTH, W>(c, a, i << W);
+    tc_enter_wide<NTH>(c, [&](int rw) { return base + elem(rw, i) * lc; }, tmp);
+    tc_build_table<NTH, W>(c, i << W);
   }
-  int a = 0;
   if (nwin <= 0) {
-    TC_EACH_ROW { big_copy<NTH>(tc_h<NTH>(c, a, rw), dc.ONEM.d0); big_copy<NTH>(tc_h<NTH>(c, a ^ 1, rw), dc.ONEM.d1); }
+    tc_set_one<NTH>(c);
   } else {
     for (int wi = nwin - 1; wi >= 0; wi--) {
-      if (wi < nwin - 1) for (int s = 0; s < W; s++) { tc_sqr_inplace<NTH>(c, a); a ^= 1; }
+      if (wi < nwin - 1) for (int s = 0; s < W; s++) tc_sqr_inplace<NTH>(c);
       for (int i = 0; i < gsz; i++) {
-        if (wi == nwin - 1 && i == 0) {
-          TC_EACH_ROW {
-            const int d = digit(rw, 0, wi);
-            big_copy<NTH>(tc_h<NTH>(c, a, rw), tc_tbl<NTH>(c, d, 0, rw));
-            big_copy<NTH>(tc_h<NTH>(c, a ^ 1, rw), tc_tbl<NTH>(c, d, 1, rw));
-          }
-        } else {
-          tc_mul_inplace<NTH>(c, a, [&](int rw) { return tc_tbl<NTH>(c, (i << W) + digit(rw, i, wi), 0, rw); },
-                              [&](int rw) { return tc_tbl<NTH>(c, (i << W) + digit(rw, i, wi), 1, rw); });
-          a ^= 1;
-        }
+        if (wi == nwin - 1 && i == 0) tc_tbl_load_f<NTH>(c, [&](int rw) { return digit(rw, 0, wi); });
+        else tc_mul_inplace<NTH>(c, [&](int rw) { return tc_tbl<NTH>(c, (i << W) + digit(rw, i, wi), 0, rw); },
+                                 [&](int rw) { return tc_tbl<NTH>(c, (i << W) + digit(rw, i, wi), 1, rw); });
       }
     }
   }
-  tc_exit_plain<NTH>(c, a, [&](int rw) { return out + g[rw] * lc; }, store);
+  tc_exit_plain<NTH>(c, [&](int rw) { return out + g[rw] * lc; }, store);
 }
 
-// one prime side: m_x = L(c^(x-1) mod x^2) * h mod x  -> returns the index of the half-buffer that holds it (NTP tiles)
+// ------------------------------------------------------------------------------------------------
+// raw_decrypt with CRT (phe/paillier.py:328-374) on the tensor-core path: the same program as prog_decrypt_digit
+// (pai_digit.cuh), every product modulo p^2 / q^2 through tc_op.
+// one prime side: m_x = L(c^(x-1) mod x^2) * h mod x  -> NTP tiles in the shared buffer X (buffer 0)
 template <int NTP, int W>
-PAI_DEV int tc_decrypt_half(TcCtx<NTP>& c, DSideC<NTP>& S, const uint8_t* bands, const uint32_t* cbase, const long* g) {
+PAI_DEV void tc_decrypt_half(TcCtx<NTP>& c, DSideC<NTP>& S, const uint8_t* bands, const uint32_t* cbase, const long* g) {
   DigitEnv& dc = S.dc;
   c.dc = &dc;
   c.band[0] = bands;
@@ -892,26 +959,21 @@ PAI_DEV int tc_decrypt_half(TcCtx<NTP>& c, DSideC<NTP>& S, const uint8_t* bands,
   for (int i = 0; i < 4; i++) {
     tc_op<NTP, false>(
         c, [&](int rw) { Opnd o; o.p = (u4*)(cbase + g[rw] * lc + (size_t)i * 8 * NTP); o.s = 1; return o; }, [&](int) { return dc.ZERO; },
-        [&](int) { return Ek[i].d0; }, [&](int) { return Ek[i].d1; }, 0, 1);
-    if (i == 0) tc_tbl_store<NTP>(c, 0, 1);
+        [&](int) { return Ek[i].d0; }, [&](int) { return Ek[i].d1; });
+    if (i == 0) tc_tbl_store<NTP>(c, 0);
     else TC_EACH_ROW {
       DNum acc, add;
       acc.d0 = tc_tbl<NTP>(c, 0, 0, rw); acc.d1 = tc_tbl<NTP>(c, 0, 1, rw);
-      add.d0 = tc_h<NTP>(c, 1, rw); add.d1 = tc_h<NTP>(c, 0, rw);
+      add.d0 = tc_h<NTP>(c, 0, rw); add.d1 = tc_h<NTP>(c, 1, rw);
       dadd<NTP>(acc, add, dc.N);
     }
   }
-  int a = 0;
-  tc_tbl_load<NTP>(c, 0, a);
-  if (S.nwin <= 0) {
-    TC_EACH_ROW { big_copy<NTP>(tc_h<NTP>(c, a, rw), dc.ONEM.d0); big_copy<NTP>(tc_h<NTP>(c, a ^ 1, rw), dc.ONEM.d1); }
-  } else {
-    a = tc_pow_fixed<NTP, W>(c, a, S.e, 8 * NTP, S.nwin);
-  }
-  tc_mul_inplace<NTP>(c, a, [&](int) { return dc.ONE; }, [&](int) { return dc.ZERO; });       // plain digits u = u0 + x*u1
-  a ^= 1;
+  tc_tbl_load<NTP>(c, 0);
+  if (S.nwin <= 0) tc_set_one<NTP>(c);
+  else tc_pow_fixed<NTP, W>(c, S.e, 8 * NTP, S.nwin);
+  tc_mul_inplace<NTP>(c, [&](int) { return dc.ONE; }, [&](int) { return dc.ZERO; });          // plain digits u = u0 + x*u1
   TC_EACH_ROW {
-    Opnd u0 = tc_h<NTP>(c, a, rw), u1 = tc_h<NTP>(c, a ^ 1, rw);
+    Opnd u0 = tc_h<NTP>(c, 0, rw), u1 = tc_h<NTP>(c, 1, rw);
     // L(u) = (u-1)//x = u1 if u0 >= 1;  u0 == 0: u1 - 1, and -1 = x - 1 (mod x) if u1 == 0   (pai_digit.cuh)
     uint32_t u0z = big_is_zero<NTP>(u0);
     uint32_t u1z = big_is_zero<NTP>(u1);
@@ -927,19 +989,18 @@ PAI_DEV int tc_decrypt_half(TcCtx<NTP>& c, DSideC<NTP>& S, const uint8_t* bands,
     }
     mont_mul<NTP>(u0, u1, S.hM, dc.N, dc.NI);                              // L * h mod x  (over u0's buffer)
   }
-  return a;
 }
 
 template <int NTP, int W>
 PAI_DEV void tc_decrypt_rows(TcCtx<NTP>& c, DSideC<NTP>& P, DSideC<NTP>& Qs, const Opnd& pinvqM, const uint8_t* bands,
                              const uint32_t* cbase, uint32_t* out, const long* g, const bool* store) {
   const int ln = 16 * NTP;
-  int ip = tc_decrypt_half<NTP, W>(c, P, bands, cbase, g);
-  TC_EACH_ROW { if (store[rw]) store_row(out + g[rw] * ln, tc_h<NTP>(c, ip, rw), 2 * NTP); }     // m_p -> low half of the row
-  int iq = tc_decrypt_half<NTP, W>(c, Qs, bands + 2 * tc_band_bytes(NTP), cbase, g);
+  tc_decrypt_half<NTP, W>(c, P, bands, cbase, g);
+  TC_EACH_ROW { if (store[rw]) store_row(out + g[rw] * ln, tc_h<NTP>(c, 0, rw), 2 * NTP); }      // m_p -> low half of the row
+  tc_decrypt_half<NTP, W>(c, Qs, bands + 2 * tc_band_bytes(NTP), cbase, g);
   TC_EACH_ROW {
     uint32_t* out_row = out + g[rw] * ln;
-    Opnd mq = tc_h<NTP>(c, iq, rw), mp = tc_h<NTP>(c, iq ^ 1, rw), uo = tc_a<NTP>(c, rw);
+    Opnd mq = tc_h<NTP>(c, 0, rw), mp = tc_a<NTP>(c, rw), uo = tc_h<NTP>(c, 1, rw);
     if (store[rw]) load_row(mp, out_row, 2 * NTP, 2 * NTP);
     else big_copy<NTP>(mp, mq);
     // u = (m_q - m_p) * p^-1 mod q     (m_p < p < q, m_q < q)
