@@ -502,8 +502,13 @@ def leg_headline(dev, args, pb, np, key, pool):
     dev.barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = eng.launch_count() - launches0
-    enc_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
-    dec_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    enc_each = sorted(e[0].elapsed_time(e[1]) for e in ev)
+    dec_each = sorted(e[1].elapsed_time(e[2]) for e in ev)
+    spread = {"encrypt_ms": {"min": enc_each[0], "median": enc_each[len(enc_each) // 2], "max": enc_each[-1]},
+              "decrypt_ms": {"min": dec_each[0], "median": dec_each[len(dec_each) // 2], "max": dec_each[-1]},
+              "note": "per-step device times of rank 0 (the reported value is the mean over the K steps, max over ranks)"}
+    enc_ms = sum(enc_each) / args.steps
+    dec_ms = sum(dec_each) / args.steps
     enc_ms, dec_ms = dev.max_over_ranks([enc_ms, dec_ms])
     clocks = sampler.stop() if dev.rank == 0 else None
 
@@ -556,7 +561,7 @@ def leg_headline(dev, args, pb, np, key, pool):
                   "vs_limb_e2e": None if e2e is None else {"encrypt": Bp / (t1 - t0) / e2e["value"],
                                                            "decrypt": Bp / (t2 - t1) / e2e["decrypts_per_s"]}}
         del ml, rl, cl, dl
-    res = {"enc_ms": enc_ms, "dec_ms": dec_ms, "t_wall": t_wall, "launches": launches, "clocks": clocks, "e2e": e2e,
+    res = {"enc_ms": enc_ms, "dec_ms": dec_ms, "spread": spread, "t_wall": t_wall, "launches": launches, "clocks": clocks, "e2e": e2e,
            "e2e_python": e2e_py, "parity": parity, "ln": ln, "lc": lc, "wave_enc": pub.wave(), "wave_dec": priv.wave(),
            "enc_path": pub.kernel_path(), "dec_path": priv.kernel_path()}
     return res, (pub, priv, d_m, d_r, d_c, d_d)
@@ -999,7 +1004,7 @@ def main():
         "metric": "paillier_raw_encrypts_per_sec_2048", "value": enc_per_s, "unit": "encrypts/s",
         "decrypt": {"value": dec_per_s, "unit": "decrypts/s", "ms_per_step": dec_ms},
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": enc_ms,
-        "step_ms_enc_plus_dec": enc_ms + dec_ms, "wall_s_timed_region": head["t_wall"],
+        "step_ms_enc_plus_dec": enc_ms + dec_ms, "step_ms_spread": head["spread"], "wall_s_timed_region": head["t_wall"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32 limbs (exact integer)", "data": "synthetic",
         "config": {"workload": "configs[1]: 2048-bit key, raw_encrypt + raw_decrypt, batch %d per GPU" % B, "key_bits": KEY_BITS,

@@ -31,6 +31,7 @@ with open(out + "_metrics.md", "w") as f:
         f.write("\n")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 kernel, hist, samples, total = None, Counter(), Counter(), 0
+reasons, by_op_reason, stall_cols = Counter(), {}, []
 with open(out + "_opcodes.md", "w") as f:
     def flush():
         if kernel is None or not hist:
@@ -39,14 +40,24 @@ with open(out + "_opcodes.md", "w") as f:
         for op, n in hist.most_common(28):
             f.write("| %s | %d | %d | %.1f %% |\n" % (op, n, samples[op], 100.0 * samples[op] / max(1, total)))
         f.write("\n")
+        if reasons:
+            tot = max(1, sum(reasons.values()))
+            f.write("warp-state samples by reason (all instructions): " + ", ".join("%s %.1f %%" % (k, 100.0 * v / tot) for k, v in reasons.most_common(12)) + "\n\n")
+            f.write("| opcode | top warp states while this opcode is next to issue |\n|---|---|\n")
+            for op, _ in samples.most_common(10):
+                c = by_op_reason.get(op, Counter()); t = max(1, sum(c.values()))
+                f.write("| %s | %s |\n" % (op, ", ".join("%s %.0f %%" % (k, 100.0 * v / t) for k, v in c.most_common(4))))
+            f.write("\n")
     cols = None
     for r in csv.reader(io.StringIO(src)):
         if r and r[0] == "Kernel Name":
             flush()
             kernel, hist, samples, total, cols = r[1], Counter(), Counter(), 0, None
+            reasons, by_op_reason = Counter(), {}
             continue
         if r and r[0] == "Address":
             cols = (r.index("Source"), r.index("# Samples"), r.index("Instructions Executed"))
+            stall_cols = [(i, h) for i, h in enumerate(r) if h.startswith("stall_") and "Not Issued" not in h]
             continue
         if cols and len(r) > max(cols):
             parts = r[cols[0]].split()
@@ -58,5 +69,13 @@ with open(out + "_opcodes.md", "w") as f:
             except ValueError:
                 continue
             hist[op] += n; samples[op] += s; total += s
+            for i, h in stall_cols:
+                try:
+                    v = int(r[i] or 0)
+                except (ValueError, IndexError):
+                    continue
+                if v:
+                    reasons[h] += v
+                    by_op_reason.setdefault(op, Counter())[h] += v
     flush()
 print("wrote", out + "_metrics.md", out + "_opcodes.md")

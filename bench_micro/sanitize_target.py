@@ -1,6 +1,7 @@
 """Small workload for compute-sanitizer (memcheck / racecheck): every round-2 kernel on a 1024-bit key -- tensor-core
 encrypt / decrypt / raw_mul (forced: PAI_TC=2), amortised inversion, product reduction, Straus dot product, batched
-Miller-Rabin, and the same context driven from two CUDA streams."""
+Miller-Rabin, and the same context driven from two CUDA streams.   python sanitize_target.py [rows [key_bits]]
+(2048-bit keys with PAI_TC_GROUPS=3 in the environment: three groups per CTA sharing two TMEM accumulators, x1 in L2)"""
 import os, sys
 os.environ["PAI_TC"] = "2"
 os.environ["PAI_COOP_MAX"] = "0"
@@ -9,7 +10,7 @@ import numpy as np, torch, random
 import paillier_b200 as pb, importlib
 _fx = importlib.import_module("python-paillier_b200.fixtures")
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 300
-n, p, q = _fx.fixed_key(1024)
+n, p, q = _fx.fixed_key(int(sys.argv[2]) if len(sys.argv) > 2 else 1024)
 pk = pb.PaillierPublicKey(n); sk = pb.PaillierPrivateKey(pk, p, q)
 pub, priv = pk.engine_context(), sk.engine_context()
 assert pub.kernel_path() == "tc" and priv.kernel_path() == "tc"
