@@ -167,7 +167,7 @@ constexpr int tc_tmem_cols(int groups) {
 
 // Set-up shared by the tensor-core kernels: copies the bands to shared memory, allocates TMEM and the groups' mbarriers,
 // fills in the context of the calling thread.  Returns the shared-memory address of the bands.  `entries`: user table
-// entries per thread; two more follow: the park slot and (tc_x1_global) the home of the high digit x1.
+// entries per thread; three more follow: the park slot and (tc_x1_global) the home of the high digit x1 and the W slot.
 template <int NTH>
 PAI_DEV uint8_t* tc_cta_begin(TcCtx<NTH>& c, u4* smem, const CtaId& id, int const_limbs, int nbands, const uint8_t* gbands, u4* tbl,
                               int entries, int stagger_cycles) {
@@ -188,7 +188,7 @@ PAI_DEV uint8_t* tc_cta_begin(TcCtx<NTH>& c, u4* smem, const CtaId& id, int cons
   c.band[0] = bands; c.band[1] = bands + tc_band_bytes(NTH);
   c.slots = entries;                                         // park slot = entry `entries`, x1 home = entry `entries` + 1
   c.nthr = id.nthr;
-  const size_t tbl_cta = (size_t)(entries + 2) * 4 * NTH * id.nthr;
+  const size_t tbl_cta = (size_t)(entries + 3) * 4 * NTH * id.nthr;
   (void)D;
 #if defined(PAI_HOSTSIM)
   // one call walks the TC_RL rows of the CTA (id.nthr == TC_RL); they sit in different 8-row groups of the operand

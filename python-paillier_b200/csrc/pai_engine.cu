@@ -793,7 +793,7 @@ int do_encrypt_tc(pai_pub* k, const uint32_t* m_, const uint32_t* r, uint32_t* c
   }
   rc = tc_geometry<NTH>(k, batch, g);
   if (rc) return rc;
-  rc = m->ws.get(s).tbl.ensure((size_t)g.grid * (size_t)(k->nodd + 3) * 4 * NTH * g.nthr * 16);
+  rc = m->ws.get(s).tbl.ensure((size_t)g.grid * (size_t)(k->nodd + 4) * 4 * NTH * g.nthr * 16);
   if (rc) return rc;
   B body{k->d_enc_consts, dc_enc_limbs(NTH) / 4, k->d_prog, k->nops, k->nodd, m_, r, c, batch, (u4*)m->ws.get(s).tbl.p,
          m->d_blob + dc_zero_offset(NTH), k->d_tc, k->tc_stagger, nullptr};
@@ -826,7 +826,7 @@ int do_powmod_tc(pai_pub* k, const uint32_t* base, const uint32_t* d_exp, int ex
   Geom g;
   int rc = tc_geometry_of<B, NTH>(m->device, [](int nthr) { return tc_pow_smem_bytes<NTH>(nthr); }, batch, g);
   if (rc) return rc;
-  rc = m->ws.get(s).tbl.ensure((size_t)g.grid * (((size_t)1 << W_VAR) + 2) * 4 * NTH * g.nthr * 16);
+  rc = m->ws.get(s).tbl.ensure((size_t)g.grid * (((size_t)1 << W_VAR) + 3) * 4 * NTH * g.nthr * 16);
   if (rc) return rc;
   B body{k->d_enc_consts, dc_pow_limbs(NTH) / 4, base, d_exp, exp_limbs, out, batch, (u4*)m->ws.get(s).tbl.p,
          m->d_blob + dc_zero_offset(NTH), k->d_tc, k->tc_stagger};
@@ -848,7 +848,7 @@ int do_straus_tc(pai_pub* k, const uint32_t* base, const uint32_t* d_exp, int ex
   const long ngroups = (batch + gsz - 1) / gsz;
   rc = tc_geometry_of<B, NTH>(m->device, [](int nthr) { return tc_pow_smem_bytes<NTH>(nthr); }, ngroups, g);
   if (rc) return rc;
-  rc = m->ws.get(s).tbl.ensure((size_t)g.grid * (((size_t)gsz << W_VAR) + 3) * 4 * NTH * g.nthr * 16);
+  rc = m->ws.get(s).tbl.ensure((size_t)g.grid * (((size_t)gsz << W_VAR) + 4) * 4 * NTH * g.nthr * 16);
   if (rc) return rc;
   B body{k->d_enc_consts, dc_pow_limbs(NTH) / 4, base, d_exp, exp_limbs, (int)gsz, partial, batch, (u4*)m->ws.get(s).tbl.p,
          m->d_blob + dc_zero_offset(NTH), k->d_tc, k->tc_stagger};
@@ -953,7 +953,7 @@ int do_decrypt_tc(pai_priv* k, const uint32_t* c, uint32_t* out, long batch, rt_
   }
   rc = tc_dec_geometry<NTP>(k, batch, g);
   if (rc) return rc;
-  rc = k->ws.get(s).tbl.ensure((size_t)g.grid * (((size_t)1 << W_DEC) + 2) * 4 * NTP * g.nthr * 16);
+  rc = k->ws.get(s).tbl.ensure((size_t)g.grid * (((size_t)1 << W_DEC) + 3) * 4 * NTP * g.nthr * 16);
   if (rc) return rc;
   int cq = 2 * (dside_limbs<NTP>() / 4) + 2 * NTP;
   B body{k->d_dconsts, cq, k->nwin_p, k->nwin_q, c, out, batch, (u4*)k->ws.get(s).tbl.p, k->d_tc, k->tc_stagger};

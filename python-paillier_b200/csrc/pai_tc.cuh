@@ -142,6 +142,9 @@ PAI_DEV Opnd tc_tbl(const TcCtx<NTH>& c, int e, int half, int rw) {
 }
 template <int NTH>
 PAI_DEV Opnd tc_park(const TcCtx<NTH>& c, int rw) { return tc_tbl<NTH>(c, c.slots, 0, rw); }
+// the W slot (tc_x1_global only): entry slots + 2 of the strip (slots + 1 is the home of x1)
+template <int NTH>
+PAI_DEV Opnd tc_wslot(const TcCtx<NTH>& c, int rw) { return tc_tbl<NTH>(c, c.slots + 2, 0, rw); }
 template <int NTH>
 PAI_DEV SOpnd tc_xs(const TcCtx<NTH>& c, int rw) { return to_shared(tc_h<NTH>(c, 0, rw)); }
 // x1 as the operand type of its home: shared-memory loads where it is in shared memory
@@ -503,9 +506,10 @@ PAI_DEV void tc_hi_tile(const TcCtx<NTH>& c, int rw, int j, const SOpnd& m, cons
   }
 }
 
-// E2: t = (T_hi + [T_lo != 0]) + hi + [guard > ltop] -> park (in place); carry = [t >= n]; A <- (KL - m) mod R, wtop
-template <int NTH>
-PAI_FN void tc_epi_t(const TcCtx<NTH>* c, int rw, SOpnd A, Opnd Ag, Opnd P, const DigitEnv* dc, TcRow* st) {
+// E2: t = (T_hi + [T_lo != 0]) + hi + [guard > ltop] -> park (in place); carry = [t >= n]; W = (KL - m) mod R -> A in place
+// (x1 in shared memory) or -> the thread's W slot Wd in global memory (tc_x1_global); wtop
+template <int NTH, bool WSLOT>
+PAI_FN void tc_epi_t(const TcCtx<NTH>* c, int rw, SOpnd A, Opnd Ag, Opnd P, Opnd Wd, const DigitEnv* dc, TcRow* st) {
   constexpr int BL = NTH > 8 ? NTH / 2 : NTH;                   // park tiles loaded together (register budget)
   uint32_t th[BL][8];
   PAI_UNROLL
@@ -531,7 +535,19 @@ PAI_FN void tc_epi_t(const TcCtx<NTH>* c, int rw, SOpnd A, Opnd Ag, Opnd P, cons
     }
   }
   st->carry = (cy != 0u) | (bo ^ 1u);
-  st->wtop = 1u - big_rsub<NTH>(Ag, dc->KL) + st->carry;
+  uint32_t wb;
+  if constexpr (WSLOT) {                                        // W goes to its global slot: A is about to hold x1' (P2)
+    wb = 0;
+    for (int t = 0; t < NTH; t++) {
+      uint32_t a[8], b[8], r[8];
+      ld_tile(dc->KL, t, a); ld_tile(A, t, b);
+      wb = sub8b(r, a, b, wb);
+      st_tile(Wd, t, r);
+    }
+  } else {
+    wb = big_rsub<NTH>(Ag, dc->KL);
+  }
+  st->wtop = 1u - wb + st->carry;
 }
 
 // P2 (multiplication): B = x0*y1 + x1*y0 + W;  B_lo -> A (over W), B_hi (+ wtop + [B_lo != 0]) -> bh
@@ -612,23 +628,10 @@ PAI_FN void tc_prod2_sqr(SOpnd A, SOpnd bh, SOpnd x0, X1T x1, TcRow* st) {
   for (int k = 0; k < 2 * NTH; k++) {
     int lo = k - NTH + 1 > 0 ? k - NTH + 1 : 0;
     int hc = k < NTH ? k : NTH - 1;
-    if constexpr (tc_x1_global<NTH>()) {                 // x1 in global memory: next tile requested one product ahead
-      uint32_t yn[8];
-      ld_tile(x1, k - lo, yn);
-      for (int i = lo; i <= hc; i++) {
-        uint32_t x[8], y[8];
-        PAI_UNROLL
-        for (int j = 0; j < 8; j++) y[j] = yn[j];
-        if (i < hc) ld_tile(x1, k - i - 1, yn);
-        ld_tile(x0, i, x);
-        tile_mac(acc, x, y);
-      }
-    } else {
-      for (int i = lo; i <= hc; i++) {
-        uint32_t x[8], y[8];
-        ld_tile(x0, i, x); ld_tile(x1, k - i, y);
-        tile_mac(acc, x, y);
-      }
+    for (int i = lo; i <= hc; i++) {
+      uint32_t x[8], y[8];
+      ld_tile(x0, i, x); ld_tile(x1, k - i, y);
+      tile_mac(acc, x, y);
     }
     uint32_t v[8];
     if (k < NTH) {
@@ -652,6 +655,72 @@ PAI_FN void tc_prod2_sqr(SOpnd A, SOpnd bh, SOpnd x0, X1T x1, TcRow* st) {
     acc_shift8(acc);
   }
   st->ovf2 = lo32(acc.E[0]) + acc.C[0];
+}
+
+// ---- P2 of a squaring with x1 in global memory (tc_x1_global).  Read from L2 tile by tile, each tile of x1 would cross
+// NTH times; instead x1' is staged in A for the phase -- A is free because E2 sent W to the thread's global W slot Q.
+// W comes back one tile per column (requested before the column's products), B_lo replaces it there tile by tile, and moves
+// to A (the MMA operand) when the products are done: 5*NTH tile transfers through L2 per phase instead of 10*NTH.
+// (Multiplications keep W in A and prefetch x1: one in seven products, and the staging copies cost them more than they save.)
+template <int NTH>
+PAI_DEV void tc_q_to_a(SOpnd A, Opnd Q) {
+  constexpr int BL = NTH % 4 == 0 ? 4 : (NTH % 3 == 0 ? 3 : (NTH % 2 == 0 ? 2 : 1));      // loads in flight together
+  PAI_UNROLL
+  for (int j0 = 0; j0 < NTH; j0 += BL) {
+    uint32_t t[BL][8];
+    PAI_UNROLL
+    for (int j = 0; j < BL; j++) ld_tile(Q, j0 + j, t[j]);
+    PAI_UNROLL
+    for (int j = 0; j < BL; j++) st_tile(A, j0 + j, t[j]);
+  }
+}
+template <int NTH>
+PAI_FN void tc_prod2_sqr_g(SOpnd A, Opnd Q, SOpnd bh, SOpnd x0, Opnd x1, TcRow* st) {
+  uint32_t tb = 0;
+  for (int t = 0; t < NTH; t++) {                       // x1' = 2*x1 mod R -> A, top bit tb
+    uint32_t x[8], y[8];
+    ld_tile(x1, t, x);
+    y[0] = (x[0] << 1) | tb;
+    PAI_UNROLL
+    for (int j = 1; j < 8; j++) y[j] = (x[j] << 1) | (x[j - 1] >> 31);
+    tb = x[7] >> 31;
+    st_tile(A, t, y);
+  }
+  Acc acc;
+  acc_clear(acc);
+  uint32_t nz2 = 0;
+  TcLow low; low.lowor = 0; low.top = 0;
+  for (int k = 0; k < 2 * NTH; k++) {
+    int lo = k - NTH + 1 > 0 ? k - NTH + 1 : 0;
+    int hc = k < NTH ? k : NTH - 1;
+    uint32_t w[8];
+    if (k < NTH) ld_tile(Q, k, w);
+    for (int i = lo; i <= hc; i++) {
+      uint32_t x[8], y[8];
+      ld_tile(x0, i, x); ld_tile(A, k - i, y);
+      tile_mac(acc, x, y);
+    }
+    uint32_t v[8];
+    if (k < NTH) {
+      acc_add_low(acc, w);
+      acc_resolve_low(acc, v);
+      st_tile(Q, k, v);
+      tc_low_tile(low, v, k == NTH - 1);
+      if (k == NTH - 1) { nz2 = (low.lowor | low.top) != 0u; st->ltop = ~low.top + (low.lowor == 0u ? 1u : 0u); }
+    } else {
+      if (tb) {
+        uint32_t xw[8];
+        ld_tile(x0, k - NTH, xw);
+        acc_add_low(acc, xw);
+      }
+      if (k == NTH) acc.C[0] += st->wtop + nz2;
+      acc_resolve_low(acc, v);
+      st_tile(bh, k - NTH, v);
+    }
+    acc_shift8(acc);
+  }
+  st->ovf2 = lo32(acc.E[0]) + acc.C[0];
+  tc_q_to_a<NTH>(A, Q);
 }
 
 // E4: z = B_hi' + hi' + [guard > ltop] (+ ovf2 * R) < 3n + 3, reduced modulo n in place (bh)
@@ -716,11 +785,13 @@ PAI_DEV void tc_op(TcCtx<NTH>& c, FX0 x0, FX1 x1, FY0 y0, FY1 y1) {
   TC_PROF(c, t0, 2);
   tc_gemm<NTH>(c, 1);
   TC_PROF(c, t0, 3);
-  TC_EACH_ROW tc_epi_t<NTH>(&c, rw, tc_as<NTH>(c, rw), tc_a<NTH>(c, rw), tc_park<NTH>(c, rw), c.dc, &st[rw]);
+  constexpr bool SWAP = SQR && tc_x1_global<NTH>();      // squarings with x1 in global memory stage it in A (tc_prod2_sqr_g)
+  TC_EACH_ROW tc_epi_t<NTH, SWAP>(&c, rw, tc_as<NTH>(c, rw), tc_a<NTH>(c, rw), tc_park<NTH>(c, rw), tc_wslot<NTH>(c, rw), c.dc, &st[rw]);
   tc_tmem_release<NTH>(c);
   TC_PROF(c, t0, 4);
   TC_EACH_ROW {
-    if constexpr (SQR) tc_prod2_sqr<NTH>(tc_as<NTH>(c, rw), tc_xs<NTH>(c, rw), x0(rw), x1(rw), &st[rw]);
+    if constexpr (SWAP) tc_prod2_sqr_g<NTH>(tc_as<NTH>(c, rw), tc_wslot<NTH>(c, rw), tc_xs<NTH>(c, rw), x0(rw), x1(rw), &st[rw]);
+    else if constexpr (SQR) tc_prod2_sqr<NTH>(tc_as<NTH>(c, rw), tc_xs<NTH>(c, rw), x0(rw), x1(rw), &st[rw]);
     else tc_prod2_mul<NTH>(tc_as<NTH>(c, rw), tc_xs<NTH>(c, rw), x0(rw), x1(rw), y0(rw), y1(rw), &st[rw]);
   }
   TC_PROF(c, t0, SQR ? 5 : 9);
