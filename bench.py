@@ -759,9 +759,11 @@ def leg_multi_parity(dev, args, pb, np, pool, H, load_golden):
         idx = sorted(set(idx))
         ti = torch.tensor(idx, device="cuda")
         mi, ri, ci = (to_ints(pb, np, t[ti]) for t in (gm, gr, gc))
-        assert ci == pool.oracle("enc", key, list(zip(mi, ri))), "gathered ciphertexts differ from the oracle"
-        res = {"world": dev.world, "vector_rows": total, "gathered_rows_checked_vs_gmp_oracle": len(idx), "shards_covered": dev.world,
-               "result": "bit-exact", "decrypt_of_gathered_vector_on_every_rank": None}
+        if pool is not None:
+            assert ci == pool.oracle("enc", key, list(zip(mi, ri))), "gathered ciphertexts differ from the oracle"
+        res = {"world": dev.world, "vector_rows": total, "gathered_rows_checked_vs_gmp_oracle": len(idx) if pool is not None else 0,
+               "shards_covered": dev.world, "result": "bit-exact" if pool is not None else "oracle check skipped (--no-cpu): device round trip only",
+               "decrypt_of_gathered_vector_on_every_rank": None}
     (allok,) = dev.max_over_ranks([0.0 if ok else 1.0])
     assert allok == 0.0, "a rank failed to decrypt the gathered vector"
     if res:
