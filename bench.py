@@ -350,8 +350,8 @@ def measured_int_peak():
 
 def _ncu_traffic(name):
     """DRAM bytes (read + write) per row of the named kernel from the committed `ncu --set full` capture summary
-    (profiles/r02_ncu_traffic.json, falling back to round 1's)."""
-    for fn in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+    (profiles/r02c_ncu_traffic.json: the final build; falling back to earlier captures)."""
+    for fn in ("r02c_ncu_traffic.json", "r02_ncu_traffic.json", "r01_ncu_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", fn)) as f:
                 t = json.load(f)
