@@ -20,15 +20,17 @@
  *     (host-pointer variants: until their results are back in host memory), so one context may be shared by any
  *     number of host threads.  Scratch memory (window tables, work counters, intermediate rows) is kept per
  *     (context, stream): calls on different streams run concurrently on the device without sharing any of it;
- *     each stream a context is used on costs one table workspace (about 0.5 GB at 2048-bit keys).
+ *     each stream a context is used on costs one table workspace (about 1 GB at 2048-bit keys).
  *   - Every function returns 0 on success or a negative PAI_E_* code; pai_last_error() gives text.
  *   - There is NO CPU fallback: without a CUDA device every compute call fails with PAI_E_CUDA.
  *   - Batch size needs no tuning: pai_encrypt / pai_decrypt / pai_mod_powmod_shared route a batch (or the remainder of
  *     a batch beyond whole waves of the thread-per-ciphertext kernels) of up to 0.3 wave to warp-per-ciphertext
  *     kernels with ~10x lower latency.  Environment switches, read at call time / context creation:
  *     PAI_COOP_MAX=<rows> (0 = never use the warp kernels), PAI_TC=0 (base-n digit kernels on the integer pipe instead of
- *     the tensor-core reductions; 2 = tensor-core kernels for every size they exist for, default: digit moduli >= 1024 bits), PAI_ENCRYPT_PATH=full, PAI_DECRYPT_PATH=full (full-width Montgomery kernels instead of
- *     the base-n digit kernels).  All variants return identical bits.
+ *     the tensor-core reductions; 2 = tensor-core kernels for every size they exist for, default: digit moduli >= 1024 bits),
+ *     PAI_TC_GROUPS=<1..4> (cap on the 128-thread groups per CTA of the tensor-core kernels; experiments and sanitizer runs),
+ *     PAI_ENCRYPT_PATH=full, PAI_DECRYPT_PATH=full (full-width Montgomery kernels instead of the base-n digit kernels).
+ *     All variants return identical bits.
  */
 #ifndef PAILLIER_B200_H
 #define PAILLIER_B200_H
