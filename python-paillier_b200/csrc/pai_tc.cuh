@@ -665,6 +665,7 @@ PAI_FN void tc_prod2_sqr(SOpnd A, SOpnd bh, SOpnd x0, X1T x1, TcRow* st) {
 template <int NTH>
 PAI_DEV void tc_q_to_a(SOpnd A, Opnd Q) {
   constexpr int BL = NTH % 4 == 0 ? 4 : (NTH % 3 == 0 ? 3 : (NTH % 2 == 0 ? 2 : 1));      // loads in flight together
+  static_assert(NTH % BL == 0, "whole blocks only: a partial block would run past the row");
   PAI_UNROLL
   for (int j0 = 0; j0 < NTH; j0 += BL) {
     uint32_t t[BL][8];
