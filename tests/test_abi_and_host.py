@@ -84,3 +84,46 @@ def test_build_tracks_every_device_header():
     with open(ge.__file__) as f:
         text = f.read()
     assert all('"%s"' % h in text for h in included)
+
+
+def test_tc_shared_memory_budget(tmp_path):
+    """The number of 128-thread groups a tensor-core CTA runs is decided by shared memory (pai_engine.cu: tc_geometry_of
+    takes the largest count whose buffers fit 227 KB - 128 B).  Pin the counts the measured numbers rely on, so that a
+    buffer growing by a few bytes cannot silently drop a group: 3 groups at 192/256 digits (x1 in the table strip),
+    4 groups at 64/128 digits, 1 group at 384 digits."""
+    import subprocess
+    src = tmp_path / "budget.cpp"
+    src.write_text(r'''
+#define PAI_HOSTSIM 1
+#include <cstdio>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "%s/python-paillier_b200/csrc/pai_cta.cuh"
+using namespace pai;
+template <int N> void row() {
+  for (int g = 1; g <= 4; g++)
+    printf("%%d %%d %%zu %%zu %%zu %%d\n", N, g, tc_enc_smem_bytes<N>(128 * g), tc_pow_smem_bytes<N>(128 * g), tc_dec_smem_bytes<N>(128 * g),
+           (int)tc_x1_global<N>());
+}
+int main() { row<2>(); row<4>(); row<6>(); row<8>(); row<12>(); return 0; }
+''' % ROOT)
+    exe = tmp_path / "budget"
+    subprocess.run(["g++", "-std=c++17", "-x", "c++", str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    limit = 232448 - 128                                   # cudaDevAttrMaxSharedMemoryPerBlockOptin on sm_100 minus the margin
+    fits = {}
+    for line in out:
+        if line.strip():
+            n, g, enc, pw, dec, x1g = (int(v) for v in line.split())
+            fits[(n, g)] = (enc <= limit, pw <= limit, dec <= limit, x1g)
+    best = lambda n, i: max(g for g in range(1, 5) if fits[(n, g)][i])
+    assert [fits[(n, 1)][3] for n in (2, 4, 6, 8, 12)] == [0, 0, 1, 1, 0]
+    # register budget (BodyMaxThreads) caps 192/256 digits at 3 groups; shared memory has to allow at least that many
+    assert best(8, 0) == 3 and best(8, 1) == 3 and best(8, 2) == 2      # 4096-bit-key decrypt: four bands, two groups
+    assert best(6, 0) >= 3 and best(6, 1) >= 3 and best(6, 2) >= 3
+    assert best(4, 0) == 4 and best(4, 1) == 4 and best(4, 2) == 4
+    assert best(2, 0) == 4 and best(2, 2) == 4
+    assert best(12, 0) == 1 and best(12, 1) == 1                        # (no 384-digit decrypt: keys stop at 4096 bits)
